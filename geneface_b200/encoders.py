@@ -1,0 +1,247 @@
+"""Drop-in for modules/radnerfs/encoders/{gridencoder/grid.py, shencoder/sphere_harmonics.py,
+freqencoder/freq.py, encoding.py} (reference @ 15ff4e5c): same classes, constructor arguments,
+parameter/buffer names (so reference checkpoints load) and forward semantics, on libgfrender.so.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import c_f32, check, ptr, stream_ptr
+
+_gridtype_to_id = {'hash': 0, 'tiled': 1}
+_interp_to_id = {'linear': 0, 'smoothstep': 1}
+
+
+class _grid_encode(Function):
+    @staticmethod
+    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False, gridtype=0,
+                align_corners=False, interpolation=0):
+        """grid.py:24-63.  inputs [B,D] in [0,1] -> [B, L*C]."""
+        inputs = inputs.float().contiguous()
+        B, D = inputs.shape
+        L = offsets.shape[0] - 1
+        C = embeddings.shape[1]
+        S = float(np.log2(per_level_scale))
+        H = base_resolution
+        # manual autocast handling, as grid.py:43-44
+        if torch.is_autocast_enabled() and C % 2 == 0:
+            embeddings = embeddings.to(torch.half)
+        embeddings = embeddings.contiguous()
+        dtype = 1 if embeddings.dtype == torch.half else 0
+        outputs = torch.empty(L, B, C, device=inputs.device, dtype=embeddings.dtype)
+        dy_dx = torch.empty(B, L * D * C, device=inputs.device, dtype=embeddings.dtype) if calc_grad_inputs else None
+        check(_lib.lib().gf_grid_encode_forward(ptr(inputs), ptr(embeddings), ptr(offsets), ptr(outputs), B, D, C, L, c_f32(S), H,
+                                                ptr(dy_dx), gridtype, int(align_corners), interpolation, dtype, stream_ptr()),
+              "grid_encode_forward")
+        outputs = outputs.permute(1, 0, 2).reshape(B, L * C)
+        ctx.save_for_backward(inputs, embeddings, offsets, dy_dx)
+        ctx.dims = [B, D, C, L, S, H, gridtype, interpolation]
+        ctx.align_corners = align_corners
+        return outputs
+
+    @staticmethod
+    def backward(ctx, grad):
+        """grid.py:65-89"""
+        inputs, embeddings, offsets, dy_dx = ctx.saved_tensors
+        B, D, C, L, S, H, gridtype, interpolation = ctx.dims
+        grad = grad.to(embeddings.dtype).view(B, L, C).permute(1, 0, 2).contiguous()
+        grad_embeddings = torch.zeros_like(embeddings)
+        grad_inputs = torch.zeros_like(inputs, dtype=embeddings.dtype) if dy_dx is not None else None
+        dtype = 1 if embeddings.dtype == torch.half else 0
+        check(_lib.lib().gf_grid_encode_backward(ptr(grad), ptr(inputs), ptr(embeddings), ptr(offsets), ptr(grad_embeddings), B, D, C,
+                                                 L, c_f32(S), H, ptr(dy_dx), ptr(grad_inputs), gridtype, int(ctx.align_corners),
+                                                 interpolation, dtype, stream_ptr()), "grid_encode_backward")
+        if dy_dx is not None:
+            grad_inputs = grad_inputs.to(inputs.dtype)
+        return grad_inputs, grad_embeddings, None, None, None, None, None, None, None
+
+
+grid_encode = _grid_encode.apply
+
+
+def grid_level_offsets(input_dim, num_levels, base_resolution, per_level_scale, log2_hashmap_size, align_corners):
+    """grid.py:116-128"""
+    max_params = 2 ** log2_hashmap_size
+    offsets, offset = [], 0
+    for i in range(num_levels):
+        resolution = int(np.ceil(base_resolution * per_level_scale ** i))
+        params_in_level = min(max_params, (resolution if align_corners else resolution + 1) ** input_dim)
+        params_in_level = int(np.ceil(params_in_level / 8) * 8)
+        offsets.append(offset)
+        offset += params_in_level
+    offsets.append(offset)
+    return offsets
+
+
+class GridEncoder(nn.Module):
+    def __init__(self, input_dim=3, num_levels=16, level_dim=2, per_level_scale=2, base_resolution=16, log2_hashmap_size=19,
+                 desired_resolution=None, gridtype='hash', align_corners=False, interpolation='linear'):
+        super().__init__()
+        if desired_resolution is not None:
+            per_level_scale = np.exp2(np.log2(desired_resolution / base_resolution) / (num_levels - 1))
+        self.input_dim = input_dim
+        self.num_levels = num_levels
+        self.level_dim = level_dim
+        self.per_level_scale = per_level_scale
+        self.log2_hashmap_size = log2_hashmap_size
+        self.base_resolution = base_resolution
+        self.output_dim = num_levels * level_dim
+        self.gridtype = gridtype
+        self.gridtype_id = _gridtype_to_id[gridtype]
+        self.interpolation = interpolation
+        self.interp_id = _interp_to_id[interpolation]
+        self.align_corners = align_corners
+        offsets = grid_level_offsets(input_dim, num_levels, base_resolution, per_level_scale, log2_hashmap_size, align_corners)
+        self.register_buffer('offsets', torch.from_numpy(np.array(offsets, dtype=np.int32)))
+        self.n_params = offsets[-1] * level_dim
+        self.embeddings = nn.Parameter(torch.empty(offsets[-1], level_dim))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.embeddings.data.uniform_(-1e-4, 1e-4)
+
+    def __repr__(self):
+        return (f"GridEncoder: input_dim={self.input_dim} num_levels={self.num_levels} level_dim={self.level_dim} "
+                f"resolution={self.base_resolution} -> {int(round(self.base_resolution * self.per_level_scale ** (self.num_levels - 1)))} "
+                f"per_level_scale={self.per_level_scale:.4f} params={tuple(self.embeddings.shape)} gridtype={self.gridtype} "
+                f"align_corners={self.align_corners} interpolation={self.interpolation}")
+
+    def forward(self, inputs, bound=1):
+        inputs = (inputs + bound) / (2 * bound)
+        prefix_shape = list(inputs.shape[:-1])
+        inputs = inputs.view(-1, self.input_dim)
+        outputs = grid_encode(inputs, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution, inputs.requires_grad,
+                              self.gridtype_id, self.align_corners, self.interp_id)
+        return outputs.view(prefix_shape + [self.output_dim])
+
+    @torch.no_grad()
+    def grad_total_variation(self, weight=1e-7, inputs=None, bound=1, B=1000000):
+        """grid.py:164-184"""
+        D, C, L = self.input_dim, self.embeddings.shape[1], self.offsets.shape[0] - 1
+        S, H = float(np.log2(self.per_level_scale)), self.base_resolution
+        if inputs is None:
+            inputs = torch.rand(B, self.input_dim, device=self.embeddings.device)
+        else:
+            inputs = ((inputs + bound) / (2 * bound)).view(-1, self.input_dim)
+            B = inputs.shape[0]
+        if self.embeddings.grad is None:
+            raise ValueError('grad is None, should be called after loss.backward() and before optimizer.step()!')
+        check(_lib.lib().gf_grad_total_variation(ptr(inputs.float().contiguous()), ptr(self.embeddings), ptr(self.embeddings.grad),
+                                                 ptr(self.offsets), c_f32(weight), B, D, C, L, c_f32(S), H, self.gridtype_id,
+                                                 int(self.align_corners), stream_ptr()), "grad_total_variation")
+
+
+class _sh_encoder(Function):
+    @staticmethod
+    def forward(ctx, inputs, degree, calc_grad_inputs=False):
+        """sphere_harmonics.py:14-37"""
+        inputs = inputs.float().contiguous()
+        B, input_dim = inputs.shape
+        output_dim = degree ** 2
+        outputs = torch.empty(B, output_dim, dtype=inputs.dtype, device=inputs.device)
+        dy_dx = torch.empty(B, input_dim * output_dim, dtype=inputs.dtype, device=inputs.device) if calc_grad_inputs else None
+        check(_lib.lib().gf_sh_encode_forward(ptr(inputs), ptr(outputs), B, input_dim, degree, ptr(dy_dx), stream_ptr()), "sh_encode_forward")
+        ctx.save_for_backward(inputs, dy_dx)
+        ctx.dims = [B, input_dim, degree]
+        return outputs
+
+    @staticmethod
+    def backward(ctx, grad):
+        inputs, dy_dx = ctx.saved_tensors
+        if dy_dx is None:
+            return None, None, None
+        grad = grad.float().contiguous()
+        B, input_dim, degree = ctx.dims
+        grad_inputs = torch.zeros_like(inputs)
+        check(_lib.lib().gf_sh_encode_backward(ptr(grad), ptr(inputs), B, input_dim, degree, ptr(dy_dx), ptr(grad_inputs), stream_ptr()),
+              "sh_encode_backward")
+        return grad_inputs, None, None
+
+
+sh_encode = _sh_encoder.apply
+
+
+class SHEncoder(nn.Module):
+    def __init__(self, input_dim=3, degree=4):
+        super().__init__()
+        self.input_dim = input_dim
+        self.degree = degree
+        self.output_dim = degree ** 2
+        assert self.input_dim == 3, "SH encoder only support input dim == 3"
+        assert self.degree > 0 and self.degree <= 8, "SH encoder only supports degree in [1, 8]"
+
+    def __repr__(self):
+        return f"SHEncoder: input_dim={self.input_dim} degree={self.degree}"
+
+    def forward(self, inputs, size=1):
+        inputs = inputs / size
+        prefix_shape = list(inputs.shape[:-1])
+        inputs = inputs.reshape(-1, self.input_dim)
+        outputs = sh_encode(inputs, self.degree, inputs.requires_grad)
+        return outputs.reshape(prefix_shape + [self.output_dim])
+
+
+class _freq_encoder(Function):
+    @staticmethod
+    def forward(ctx, inputs, degree, output_dim):
+        """freq.py:15-35"""
+        if not inputs.is_cuda:
+            inputs = inputs.cuda()
+        inputs = inputs.float().contiguous()
+        B, input_dim = inputs.shape
+        outputs = torch.empty(B, output_dim, dtype=inputs.dtype, device=inputs.device)
+        check(_lib.lib().gf_freq_encode_forward(ptr(inputs), B, input_dim, degree, output_dim, ptr(outputs), stream_ptr()), "freq_encode_forward")
+        ctx.save_for_backward(inputs, outputs)
+        ctx.dims = [B, input_dim, degree, output_dim]
+        return outputs
+
+    @staticmethod
+    def backward(ctx, grad):
+        grad = grad.float().contiguous()
+        inputs, outputs = ctx.saved_tensors
+        B, input_dim, degree, output_dim = ctx.dims
+        grad_inputs = torch.zeros_like(inputs)
+        check(_lib.lib().gf_freq_encode_backward(ptr(grad), ptr(outputs), B, input_dim, degree, output_dim, ptr(grad_inputs), stream_ptr()),
+              "freq_encode_backward")
+        return grad_inputs, None, None
+
+
+freq_encode = _freq_encoder.apply
+
+
+class FreqEncoder(nn.Module):
+    def __init__(self, input_dim=3, degree=4):
+        super().__init__()
+        self.input_dim = input_dim
+        self.degree = degree
+        self.output_dim = input_dim + input_dim * 2 * degree
+
+    def __repr__(self):
+        return f"FreqEncoder: input_dim={self.input_dim} degree={self.degree} output_dim={self.output_dim}"
+
+    def forward(self, inputs, **kwargs):
+        prefix_shape = list(inputs.shape[:-1])
+        inputs = inputs.reshape(-1, self.input_dim)
+        outputs = freq_encode(inputs, self.degree, self.output_dim)
+        return outputs.reshape(prefix_shape + [self.output_dim])
+
+
+def get_encoder(encoding, input_dim=3, multires=6, degree=4, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
+                desired_resolution=2048, align_corners=False, interpolation='linear', **kwargs):
+    """encoding.py:6-34"""
+    if encoding == 'None':
+        return (lambda x, **kw: x), input_dim
+    if encoding == 'frequency':
+        encoder = FreqEncoder(input_dim=input_dim, degree=multires)
+    elif encoding == 'spherical_harmonics':
+        encoder = SHEncoder(input_dim=input_dim, degree=degree)
+    elif encoding in ('hashgrid', 'tiledgrid'):
+        encoder = GridEncoder(input_dim=input_dim, num_levels=num_levels, level_dim=level_dim, base_resolution=base_resolution,
+                              log2_hashmap_size=log2_hashmap_size, desired_resolution=desired_resolution,
+                              gridtype='hash' if encoding == 'hashgrid' else 'tiled', align_corners=align_corners,
+                              interpolation=interpolation, **kwargs)
+    else:
+        raise NotImplementedError('Unknown encoding mode, choose from [None, frequency, spherical_harmonics, hashgrid, tiledgrid]')
+    return encoder, encoder.output_dim

@@ -1,0 +1,225 @@
+/*
+ * gfrender.h -- C ABI of libgfrender.so, the B200-native (sm_100a) replacement for the
+ * RAD-NeRF hot path of yerfor/GeneFace.
+ *
+ * Every entry point takes raw DEVICE pointers, sizes and scalars plus an explicit CUDA
+ * stream; there are no torch types anywhere in this header.  Return value: 0 on success,
+ * negative on error (gf_last_error() returns a thread-local description).  The caller
+ * allocates every output (SURVEY.md section 8b "Ownership"); kernels never allocate, free or
+ * retain pointers, except the opaque GfModel which owns a packed copy of the weights.
+ *
+ * Each declaration cites the reference interface it replaces (paths under the reference
+ * tree, yerfor/GeneFace @ 15ff4e5c).  Argument order follows the reference's pybind
+ * functions so that a binding is a 1:1 forward (INTEGRATION.md shows the ctypes stub).
+ */
+#ifndef GFRENDER_H_
+#define GFRENDER_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GF_API __attribute__((visibility("default")))
+#else
+#define GF_API
+#endif
+
+typedef void* gf_stream_t; /* cudaStream_t (CUstream); NULL = legacy default stream */
+
+#define GF_OK 0
+#define GF_ERR_INVALID -22   /* bad argument (EINVAL) */
+#define GF_ERR_CUDA -5       /* CUDA runtime error (EIO) */
+#define GF_ERR_UNSUPPORTED -95
+
+GF_API const char* gf_last_error(void);
+GF_API int gf_version(void);
+/* 1 when a CUDA device with compute capability 10.x is current, else 0 (no exception). */
+GF_API int gf_device_ok(void);
+
+/* ------------------------------------------------------------------------------------
+ * _raymarching_face   modules/radnerfs/raymarching/src/raymarching.h:7-20
+ * ---------------------------------------------------------------------------------- */
+/* raymarching.h:7   near_far_from_aabb(rays_o, rays_d, aabb, N, min_near, nears, fars) */
+GF_API int gf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                                 float min_near, float* nears, float* fars, gf_stream_t stream);
+/* raymarching.h:8   sph_from_ray(rays_o, rays_d, radius, N, coords) */
+GF_API int gf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                           gf_stream_t stream);
+/* raymarching.h:9   morton3D(coords, N, indices) */
+GF_API int gf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, gf_stream_t stream);
+/* raymarching.h:10  morton3D_invert(indices, N, coords) */
+GF_API int gf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, gf_stream_t stream);
+/* raymarching.h:11  packbits(grid, N, density_thresh, bitfield)   N = C*H^3/8 bytes */
+GF_API int gf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, gf_stream_t stream);
+/* raymarching.h:12  morton3D_dilation(grid, C, H, grid_dilation) */
+GF_API int gf_morton3D_dilation(const float* grid, uint32_t C, uint32_t H, float* grid_dilation, gf_stream_t stream);
+/* raymarching.h:14  march_rays_train(...)  xyzs/dirs/deltas must be zero-filled by the caller;
+ * counter is int32[2] (points, rays) and is advanced atomically. */
+GF_API int gf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                               float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                               const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                               int32_t* rays, int32_t* counter, const float* noises, gf_stream_t stream);
+/* raymarching.h:15  march_rays_train_backward(...)  accumulates into grad_rays_o/d */
+GF_API int gf_march_rays_train_backward(const float* grad_xyzs, const float* grad_dirs, const int32_t* rays,
+                                        const float* deltas, uint32_t N, uint32_t M, float* grad_rays_o,
+                                        float* grad_rays_d, gf_stream_t stream);
+/* raymarching.h:16  composite_rays_train_forward(...) */
+GF_API int gf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* ambient,
+                                           const float* deltas, const int32_t* rays, uint32_t M, uint32_t N,
+                                           float T_thresh, float* weights_sum, float* ambient_sum, float* depth,
+                                           float* image, gf_stream_t stream);
+/* raymarching.h:17  composite_rays_train_backward(...) */
+GF_API int gf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_ambient_sum,
+                                            const float* grad_image, const float* sigmas, const float* rgbs,
+                                            const float* ambient, const float* deltas, const int32_t* rays,
+                                            const float* weights_sum, const float* ambient_sum, const float* image,
+                                            uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
+                                            float* grad_rgbs, float* grad_ambient, gf_stream_t stream);
+/* raymarching.h:19  march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma,
+ *                              max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, noises) */
+GF_API int gf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                         const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                         uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars,
+                         float* xyzs, float* dirs, float* deltas, const float* noises, gf_stream_t stream);
+/* raymarching.h:20  composite_rays(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas,
+ *                                  weights_sum, depth, image)   in place on the last five + rays_alive/rays_t */
+GF_API int gf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                             const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                             float* depth, float* image, gf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * _gridencoder   modules/radnerfs/encoders/gridencoder/src/gridencoder.h:11-14
+ * dtype: 0 = float32 table/outputs, 1 = float16 table/outputs (autocast path, grid.py:43-44)
+ * ---------------------------------------------------------------------------------- */
+/* gridencoder.h:11  grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, dy_dx,
+ *                                       gridtype, align_corners, interp)   outputs [L,B,C]; dy_dx [B,L*D*C] or NULL */
+GF_API int gf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets, void* outputs,
+                                  uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, void* dy_dx,
+                                  uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
+                                  gf_stream_t stream);
+/* gridencoder.h:12  grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H,
+ *                                        dy_dx, grad_inputs, gridtype, align_corners, interp) */
+GF_API int gf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings,
+                                   const int32_t* offsets, void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C,
+                                   uint32_t L, float S, uint32_t H, const void* dy_dx, void* grad_inputs,
+                                   uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
+                                   gf_stream_t stream);
+/* gridencoder.h:14  grad_total_variation(inputs, embeddings, grad, offsets, weight, B, D, C, L, S, H,
+ *                                        gridtype, align_corners)   float32 only */
+GF_API int gf_grad_total_variation(const float* inputs, const float* embeddings, float* grad, const int32_t* offsets,
+                                   float weight, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                   uint32_t gridtype, int align_corners, gf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * _shencoder   modules/radnerfs/encoders/shencoder/src/shencoder.h:8-9   (float32)
+ * ---------------------------------------------------------------------------------- */
+GF_API int gf_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t D, uint32_t degree,
+                                float* dy_dx, gf_stream_t stream);
+GF_API int gf_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t degree,
+                                 const float* dy_dx, float* grad_inputs, gf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * _freqencoder   modules/radnerfs/encoders/freqencoder/src/freqencoder.h:8-9
+ * ---------------------------------------------------------------------------------- */
+GF_API int gf_freq_encode_forward(const float* inputs, uint32_t B, uint32_t D, uint32_t degree, uint32_t C,
+                                  float* outputs, gf_stream_t stream);
+GF_API int gf_freq_encode_backward(const float* grad, const float* outputs, uint32_t B, uint32_t D, uint32_t degree,
+                                   uint32_t C, float* grad_inputs, gf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fused frame renderer: replaces the eval branch of NeRFRenderer.render()
+ * (modules/radnerfs/renderer.py:263-367) and RADNeRFTorso.render()
+ * (modules/radnerfs/radnerf_torso.py:86-198) -- ray generation, aabb test, occupancy
+ * marching, 3D grid -> ambient MLP -> 2D grid -> sigma MLP -> SH -> colour MLP, alpha
+ * compositing, torso layer and background mix -- without the host-driven loop.
+ * ---------------------------------------------------------------------------------- */
+typedef struct GfModel GfModel;
+
+/* Raw device pointers to the reference's state_dict tensors.  Not retained
+ * after gf_model_create returns (weights are repacked into the model's own buffers);
+ * the three grid tables and the bitfields ARE referenced in place (no copy). */
+typedef struct GfModelDesc {
+    /* geometry / hyper-parameters */
+    float bound;                 /* hparams['bound']                       renderer.py:66 */
+    uint32_t cascade;            /* 1 + ceil(log2(bound))                  renderer.py:67 */
+    uint32_t grid_size;          /* H, hparams['grid_size']                renderer.py:68 */
+    float min_near;              /* renderer.py:71 */
+    float aabb[6];               /* aabb_infer                             renderer.py:78-81 */
+    uint32_t gridtype;           /* 0 hash, 1 tiled                        grid.py:14-17 */
+    uint32_t interp;             /* 0 linear, 1 smoothstep                 grid.py:19-22 */
+    uint32_t hidden_dim;         /* 128 (64 also supported)                base.yaml:91-98 */
+    uint32_t cond_dim;           /* cond_out_dim = 64 */
+    uint32_t ind_dim;            /* individual_embedding_dim (0 or 4) */
+    /* head field */
+    const uint8_t* density_bitfield;   /* [cascade*H^3/8] */
+    const float* pos_embeddings;  const int32_t* pos_offsets;  float pos_S; uint32_t pos_H;   /* 3D grid, L=16,C=2 */
+    const float* amb_embeddings;  const int32_t* amb_offsets;  float amb_S; uint32_t amb_H;   /* 2D grid */
+    const float* ambient_w0; const float* ambient_w1; const float* ambient_w2;   /* [h,32+cond] [h,h] [2,h] */
+    const float* sigma_w0;   const float* sigma_w1;   const float* sigma_w2;     /* [h,64] [h,h] [1+geo,h] */
+    const float* color_w0;   const float* color_w1;                              /* [h,16+geo+ind] [3,h] */
+    uint32_t geo_feat_dim;       /* 128 */
+    const float* ind_code;       /* individual_embeddings[0]  [ind_dim] or NULL */
+    /* torso (all NULL/0 for head-only) */
+    uint32_t has_torso;
+    const float* density_grid_torso;   /* [H*H] */
+    float density_thresh_torso;        /* min(density_thresh_torso, mean_density_torso)  radnerf_torso.py:166 */
+    float torso_shrink;                /* hparams['torso_shrink'] */
+    const float* torso_embeddings; const int32_t* torso_offsets; float torso_S; uint32_t torso_H;
+    const float* torso_deform_w0; const float* torso_deform_w1; const float* torso_deform_w2;  /* [64,104] [64,64] [2,64] */
+    const float* torso_canon_w0;  const float* torso_canon_w1;  const float* torso_canon_w2;   /* [32,136] [32,32] [4,32] */
+    uint32_t torso_ind_dim;            /* 8 */
+    const float* torso_ind_code;       /* torso_individual_codes[0] */
+} GfModelDesc;
+
+GF_API int gf_model_create(const GfModelDesc* desc, GfModel** out, gf_stream_t stream);
+GF_API void gf_model_destroy(GfModel* m);
+/* bytes of the packed parameter blob (what rank 0 broadcasts once) */
+GF_API uint64_t gf_model_packed_bytes(const GfModel* m);
+
+/* Per-frame inputs.  Either give explicit rays (drop-in for render(rays_o, rays_d, ...)) or
+ * set rays_o = rays_d = NULL and give pose + intrinsics (rays are generated in-kernel,
+ * utils.py:282-363).  bg_color may be NULL (=> 1.0, renderer.py:354-355). */
+typedef struct GfFrame {
+    uint32_t H, W;               /* N = H*W rays */
+    const float* rays_o;         /* [N,3] or NULL */
+    const float* rays_d;         /* [N,3] or NULL */
+    float pose[12];              /* c2w rows 0..2 of the 4x4 (used when rays are NULL) */
+    float intrinsics[4];         /* fx, fy, cx, cy */
+    const float* cond_feat;      /* [cond_dim] device: output of cal_cond_feat (radnerf.py:61-71) */
+    const float* bg_color;       /* [N,3] device or NULL */
+    const float* bg_coords;      /* [N,2] device or NULL (=> generated, utils.py:273-278) */
+    float torso_pose[6];         /* convert_poses(pose)  (utils.py:263-269) */
+    float dt_gamma;              /* render(dt_gamma=...) */
+    uint32_t max_steps;          /* render(max_steps=...) */
+    float T_thresh;              /* 1e-4 default */
+    uint32_t precision;          /* 0 = fp32 SIMT (reference arithmetic), 1 = fp16 tensor cores (tcgen05) */
+} GfFrame;
+
+typedef struct GfOut {
+    float* rgb_map;              /* [N,3] clamped composite            renderer.py:357-365 */
+    float* depth_map;            /* [N]                                renderer.py:361-364 */
+    float* weights_sum;          /* [N] or NULL */
+    float* torso_alpha_map;      /* [N] or NULL                        radnerf_torso.py:187 */
+    float* torso_rgb_map;        /* [N,3] or NULL                      radnerf_torso.py:188 */
+    int32_t* n_samples;          /* [N] per-ray composited sample count or NULL (parity/diagnostics) */
+    uint8_t* rgb8;               /* [N,3] uint8 (rgb*255) or NULL      base_nerf_infer.py:97-101 */
+    uint64_t* counters;          /* device uint64[4]: samples evaluated, torso pixels, S_total, launches; or NULL */
+} GfOut;
+
+/* Standalone field evaluation = the `self(xyzs, dirs, cond_feat, ind_code)` call inside the reference
+ * loop (renderer.py:342 -> radnerf.py:73-105).  xyzs, dirs [M,3]; sigmas [M]; rgbs [M,3]; ambient [M,2] or NULL. */
+GF_API int gf_field_forward(const GfModel* model, const float* xyzs, const float* dirs, const float* cond_feat, uint32_t M,
+                            float* sigmas, float* rgbs, float* ambient, uint32_t precision, gf_stream_t stream);
+
+/* workspace the caller owns: gf_render_workspace_bytes(N) bytes of device memory */
+GF_API uint64_t gf_render_workspace_bytes(uint32_t N);
+GF_API int gf_render_frame(const GfModel* model, const GfFrame* frame, const GfOut* out, void* workspace,
+                           uint64_t workspace_bytes, gf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFRENDER_H_ */
