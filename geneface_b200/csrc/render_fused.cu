@@ -560,6 +560,12 @@ __global__ void k_finish(FinishArgs a, RayState st) {
     if (a.n_samples) a.n_samples[n] = st.nsamp[n];
 }
 
+__global__ void k_hist_out(const uint32_t* __restrict__ ctl, uint32_t max_steps, uint32_t* __restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > max_steps) return;
+    out[k] = k == 0 ? ctl[CTL_STOTAL] : ctl[CTL_HIST + k];
+}
+
 __global__ void k_counters_out(const uint32_t* __restrict__ ctl, const unsigned long long* __restrict__ stat, uint64_t* __restrict__ out, uint32_t launches) {
     if (threadIdx.x || blockIdx.x) return;
     out[0] = stat[0];
@@ -896,6 +902,7 @@ GF_API int gf_render_frame(const GfModel* model, const GfFrame* f, const GfOut* 
     fa.n_samples = o->n_samples; fa.rgb8 = o->rgb8;
     k_finish<<<div_up(N, 256), 256, 0, st>>>(fa, w.st);
     launches++;
+    if (o->term_hist) k_hist_out<<<div_up(f->max_steps + 1, 256), 256, 0, st>>>(w.ctl, f->max_steps, o->term_hist);
     if (o->counters) { k_counters_out<<<1, 32, 0, st>>>(w.ctl, w.stat, o->counters, launches + 1); }
     return check_launch("render_frame(finish)");
 }

@@ -128,7 +128,8 @@ class GridEncoder(nn.Module):
             B = inputs.shape[0]
         if self.embeddings.grad is None:
             raise ValueError('grad is None, should be called after loss.backward() and before optimizer.step()!')
-        check(_lib.lib().gf_grad_total_variation(ptr(inputs.float().contiguous()), ptr(self.embeddings), ptr(self.embeddings.grad),
+        inputs = inputs.float().contiguous()
+        check(_lib.lib().gf_grad_total_variation(ptr(inputs), ptr(self.embeddings), ptr(self.embeddings.grad),
                                                  ptr(self.offsets), c_f32(weight), B, D, C, L, c_f32(S), H, self.gridtype_id,
                                                  int(self.align_corners), stream_ptr()), "grad_total_variation")
 

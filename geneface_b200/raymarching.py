@@ -140,8 +140,9 @@ class _march_rays_train(Function):
         if step_counter is None:
             step_counter = torch.zeros(2, dtype=torch.int32, device=dev)
         noises = torch.rand(N, dtype=torch.float32, device=dev) if perturb else torch.zeros(N, dtype=torch.float32, device=dev)
+        nears, fars = nears.float().contiguous(), fars.float().contiguous()   # named: must outlive the launch
         check(_lib.lib().gf_march_rays_train(ptr(rays_o), ptr(rays_d), ptr(density_bitfield), c_f32(bound), c_f32(dt_gamma),
-                                             max_steps, N, C, H, M, ptr(nears.float().contiguous()), ptr(fars.float().contiguous()),
+                                             max_steps, N, C, H, M, ptr(nears), ptr(fars),
                                              ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(step_counter), ptr(noises),
                                              stream_ptr()), "march_rays_train")
         if force_all_rays or mean_count <= 0:
@@ -158,8 +159,9 @@ class _march_rays_train(Function):
         N, M = rays.shape[0], grad_xyzs.shape[0]
         grad_rays_o = torch.zeros(N, 3, device=rays.device)
         grad_rays_d = torch.zeros(N, 3, device=rays.device)
-        check(_lib.lib().gf_march_rays_train_backward(ptr(grad_xyzs.float().contiguous()), ptr(grad_dirs.float().contiguous()),
-                                                      ptr(rays), ptr(deltas.contiguous()), N, M, ptr(grad_rays_o), ptr(grad_rays_d),
+        grad_xyzs, grad_dirs, deltas = grad_xyzs.float().contiguous(), grad_dirs.float().contiguous(), deltas.contiguous()
+        check(_lib.lib().gf_march_rays_train_backward(ptr(grad_xyzs), ptr(grad_dirs),
+                                                      ptr(rays), ptr(deltas), N, M, ptr(grad_rays_o), ptr(grad_rays_d),
                                                       stream_ptr()), "march_rays_train_backward")
         return (grad_rays_o, grad_rays_d) + (None,) * 13
 
@@ -193,9 +195,9 @@ class _composite_rays_train(Function):
         grad_sigmas = torch.zeros_like(sigmas)
         grad_rgbs = torch.zeros_like(rgbs)
         grad_ambient = torch.zeros_like(ambient)
+        gws, gas, gim = grad_weights_sum.float().contiguous(), grad_ambient_sum.float().contiguous(), grad_image.float().contiguous()
         check(_lib.lib().gf_composite_rays_train_backward(
-            ptr(grad_weights_sum.float().contiguous()), ptr(grad_ambient_sum.float().contiguous()),
-            ptr(grad_image.float().contiguous()), ptr(sigmas), ptr(rgbs), ptr(ambient), ptr(deltas), ptr(rays), ptr(weights_sum),
+            ptr(gws), ptr(gas), ptr(gim), ptr(sigmas), ptr(rgbs), ptr(ambient), ptr(deltas), ptr(rays), ptr(weights_sum),
             ptr(ambient_sum), ptr(image), M, N, c_f32(T_thresh), ptr(grad_sigmas), ptr(grad_rgbs), ptr(grad_ambient),
             stream_ptr()), "composite_rays_train_backward")
         return grad_sigmas, grad_rgbs, grad_ambient, None, None, None
@@ -232,8 +234,9 @@ class _composite_rays(Function):
     @staticmethod
     def forward(ctx, n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2):
         """raymarching.py:401-420 (in place on rays_alive, rays_t, weights_sum, depth, image)"""
+        sigmas, rgbs = sigmas.float().contiguous(), rgbs.float().contiguous()   # named: must outlive the launch
         check(_lib.lib().gf_composite_rays(n_alive, n_step, c_f32(T_thresh), ptr(rays_alive), ptr(rays_t),
-                                           ptr(sigmas.float().contiguous()), ptr(rgbs.float().contiguous()), ptr(deltas),
+                                           ptr(sigmas), ptr(rgbs), ptr(deltas),
                                            ptr(weights_sum), ptr(depth), ptr(image), stream_ptr()), "composite_rays")
         return tuple()
 

