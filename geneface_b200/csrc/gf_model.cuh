@@ -117,5 +117,6 @@ struct GfModel {
     float* scratch_bias;    // device float[256] for gf_field_forward
     void* tc_blob;          // packed fp16 tensor-core weights (device), built lazily
     size_t tc_bytes;
+    float* tc_dbg;          // diagnostics buffer for the tcgen05 kernel (gf_tc_debug) or null
     int num_sms;
 };

@@ -217,6 +217,10 @@ typedef struct GfOut {
 GF_API int gf_field_forward(const GfModel* model, const float* xyzs, const float* dirs, const float* cond_feat, uint32_t M,
                             float* sigmas, float* rgbs, float* ambient, uint32_t precision, gf_stream_t stream);
 
+/* Diagnostics for the tcgen05 field kernel: when dbg != NULL the next precision-1 launches dump the fp32
+ * accumulators of sample tile 0 after each MMA stage into dbg (device float[9*128*144]). */
+GF_API int gf_tc_debug(GfModel* model, float* dbg);
+
 /* workspace the caller owns: gf_render_workspace_bytes(N) bytes of device memory */
 GF_API uint64_t gf_render_workspace_bytes(uint32_t N);
 GF_API int gf_render_frame(const GfModel* model, const GfFrame* frame, const GfOut* out, void* workspace,
