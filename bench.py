@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the volumetric renderer hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision fp16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is ONE 512x512 frame of the north-star synthetic workload (SURVEY.md section 8d "512x512x128"): head+torso model of the
+May configs with bound=4 (3 cascades), all-ones occupancy bitfield, dt_gamma=0, max_steps=128 -> every one of the 262,144
+rays composites exactly 128 samples (33,554,432 field evaluations per frame; asserted), plus the 2-D torso field on the lower
+image half.  Random-init weights of the exact architecture, synthetic pose/cond (no datasets or checkpoints here).
+
+value  : frames/s, whole job (all ranks), inputs (pose, cond feature window, background) resident in HBM, device-timed with
+         CUDA events over exactly K steps between barrier + synchronize; max over ranks.
+e2e    : the same metric through the public API with HOST inputs: per step pinned pose+cond -> H2D, cond encoder, fused
+         frame, RGB8 frame -> D2H into pinned memory, all inside the timed region.
+roofline: dominant kernel = the field kernel (grid gathers + MLPs); achieved = samples/frame x 1536 B (SURVEY.md 8d algorithmic
+         gather bytes per head sample) / its CUDA-event time per frame (events recorded inside gf_render_frame on the launch
+         stream); peak = MEASURED_PEAKS.json hbm_gbs.  The tables (16 MB) are L2-resident, so this is an "HBM-equivalent"
+         gather rate as the metric asks; tensor-pipe fraction is reported beside it.
+cpu_baseline: the CPU oracle (port of the reference path, OpenMP + numpy, all host threads) on a bounded sample of the SAME
+         frame (rays x 128 samples), extrapolated to frames/s.
+--impl reference: the reference's CPU implementation timed on the host cores (rank 0 only): the oracle port of the RAD-NeRF
+         path on a bounded sample per step; the vanilla AD-NeRF (modules/nerfs) port is reported in `adnerf_cpu`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "512x512 frames/sec (head+torso), 128 samples/ray"
+HEAD_SAMPLE_BYTES = 1536          # 16 lvl x 8 corners x 8 B + 16 lvl x 4 corners x 8 B
+HEAD_SAMPLE_FLOP = 178688
+TORSO_PIXEL_BYTES = 512
+H = W = 512
+MAX_STEPS = 128
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------ CPU legs
+def cpu_port_fps(n_rays=1024, threads=None):
+    """The CPU oracle (port of the reference RAD-NeRF path) on `n_rays` rays x 128 samples of the benchmark frame."""
+    import numpy as np
+    import torch
+    threads = threads or os.cpu_count()
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    torch.set_num_threads(threads)
+    from geneface_b200 import synthetic
+    from oracle import field as OF
+    model, hp = synthetic.build_model(torso=True, bitfield='F', seed=0, sigma_scale=0.25, bound=4, device='cpu')
+    sd = synthetic.state_to_numpy(model)
+    fi = synthetic.frame_inputs(H, W, device='cpu')
+    ro, rd = OF.get_rays(fi['pose'][0].numpy(), fi['intrinsics'], H, W)
+    sel = np.linspace(0, H * W - 1, n_rays).astype(np.int64)
+    ro, rd = np.ascontiguousarray(ro[sel]), np.ascontiguousarray(rd[sel])
+    fo = OF.FieldOracle(sd, bound=4.0)
+    OF.MATMUL_DTYPE = np.float32          # timing leg: fp32 GEMMs like the reference's CPU tensors
+    t0 = time.perf_counter()
+    cf = OF.cal_cond_feat(sd, fi['cond'].numpy())
+    ws, depth, img, nears, fars, ns = OF.render_head(fo, sd, ro, rd, cf, sd['density_bitfield'], 3, 128, sd['aabb_infer'], hp['min_near'], 0.0, MAX_STEPS)
+    bgc = OF.get_bg_coords(H, W)[sel]
+    bg, _, _, _ = OF.render_torso_mix(OF.TorsoOracle(sd), sd, bgc, fi['poses6'].numpy(), fi['bg_color'][0].numpy()[sel], img, ws)
+    OF.finish(img, ws, depth, nears, fars, bg)
+    dt = time.perf_counter() - t0
+    OF.MATMUL_DTYPE = np.float64
+    assert int(ns.min()) == MAX_STEPS == int(ns.max())
+    fps = 1.0 / (dt * (H * W) / n_rays)
+    return fps, dt, threads, f"{n_rays} of 262144 rays x 128 samples of the same frame (head+torso), {dt:.1f} s of CPU work, extrapolated"
+
+
+def adnerf_cpu_fps(threads=None):
+    """Vanilla AD-NeRF port (BASELINE.json configs[0]: 64x64, 64 coarse + 128 fine samples, 1 frame)."""
+    try:
+        from oracle import adnerf_port
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)}
+    return adnerf_port.time_frame(threads or os.cpu_count())
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference path on the host CPU (rank 0 only)."""
+    if rank != 0:
+        return
+    steps, warm = max(1, args.steps), args.warmup
+    n_rays = 2048
+    for _ in range(min(warm, 1)):
+        cpu_port_fps(n_rays)
+    t0 = time.perf_counter()
+    fps_list = []
+    for _ in range(steps):
+        fps, dt, threads, sample = cpu_port_fps(n_rays)
+        fps_list.append(fps)
+        if time.perf_counter() - t0 > 150:
+            break
+    k = len(fps_list)
+    value = k / sum(1.0 / f for f in fps_list)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": k, "warmup": min(warm, 1),
+            "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "RAD-NeRF head+torso 512x512, 128 samples/ray (bound=4, all-ones bitfield); CPU port of the reference path",
+                       "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "adnerf_cpu": adnerf_cpu_fps(), "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("GF_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from geneface_b200 import _lib, sequence, synthetic
+    from geneface_b200.utils import convert_poses, orbit_pose
+
+    assert torch.cuda.is_available(), "bench.py (ours) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    model, hp = synthetic.build_model(torso=True, bitfield='F', seed=0 if rank == 0 else 100 + rank, sigma_scale=0.25, bound=4, device=dev)
+    bcast_bytes = sequence.broadcast_model_(model, src=0)      # parameters reach every rank through ONE NCCL broadcast
+    fi = synthetic.frame_inputs(H, W, device=dev)
+    N = H * W
+    n_frames = args.steps + args.warmup
+    first = rank * n_frames                                    # weak scaling: every rank renders its own K frames of the sequence
+    poses = torch.stack([torch.from_numpy(orbit_pose(3.35, 10.0 * np.sin(2 * np.pi * (first + f) / 100.0))) for f in range(n_frames)])
+    g = torch.Generator().manual_seed(1234)
+    conds_all = torch.randn(300 * world + 8, 1, 204, generator=g)
+    from geneface_b200.utils import get_audio_features
+    conds = torch.stack([get_audio_features(conds_all, 2, first + f, 5) for f in range(n_frames)])       # [F,5,1,204]
+    poses_h, conds_h = poses.pin_memory(), conds.pin_memory()
+    poses_d, conds_d = poses.to(dev), conds.to(dev)
+    pose6_h = convert_poses(poses)           # host: the 6-vector travels by value in the GfFrame struct
+    bg = fi['bg_color']
+    handle = model.gf_model()
+    L = _lib.lib()
+    rgb8 = torch.empty(N, 3, dtype=torch.uint8, device=dev)
+    host_rgb8 = torch.empty(N, 3, dtype=torch.uint8).pin_memory()
+    counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    outbuf = {'rgb8': rgb8, 'counters': counters}
+
+    def frame_resident(f):
+        with torch.no_grad():
+            cf = model.cal_cond_feat(conds_d[f])
+            model.render_fused(cf, H, W, pose=poses[f], intrinsics=fi['intrinsics'], bg_color=bg, torso_pose=pose6_h[f], dt_gamma=0.0,
+                               max_steps=MAX_STEPS, precision=args.precision, want=('rgb8', 'counters'), out=outbuf)
+
+    def frame_e2e(f):
+        with torch.no_grad():
+            cond_dv = conds_h[f].to(dev, non_blocking=True)        # H2D: the frame's condition window (pinned)
+            cf = model.cal_cond_feat(cond_dv)
+            p6 = convert_poses(poses_h[f][None])[0]                 # host; pose + pose6 travel by value in the launch
+            model.render_fused(cf, H, W, pose=poses_h[f], intrinsics=fi['intrinsics'], bg_color=bg, torso_pose=p6, dt_gamma=0.0,
+                               max_steps=MAX_STEPS, precision=args.precision, want=('rgb8', 'counters'), out=outbuf)
+            host_rgb8.copy_(rgb8, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the finished frame
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up + workload assertions ----
+    for f in range(args.warmup):
+        frame_resident(f)
+    torch.cuda.synchronize()
+    c = counters.cpu().numpy()
+    samples_per_frame, torso_px, s_total, launches = int(c[0]), int(c[1]), int(c[2]), int(c[3])
+    assert samples_per_frame == N * MAX_STEPS == 33554432, f"workload must evaluate 262144 x 128 samples, got {samples_per_frame}"
+    assert s_total == MAX_STEPS and torso_px > 0
+
+    # ---- timed: resident inputs ----
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(args.steps):
+        frame_resident(args.warmup + k)
+    ev1.record()
+    barrier()
+    ms_res = ev0.elapsed_time(ev1)
+    # ---- timed: end to end (host inputs, host result) ----
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        frame_e2e(args.warmup + k)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    # ---- dominant-kernel time (events inside gf_render_frame) ----
+    _lib.check(L.gf_profile_enable(handle, 1))
+    field_ms = []
+    for k in range(min(5, args.steps)):
+        frame_resident(args.warmup + k)
+        torch.cuda.synchronize()
+        import ctypes
+        tot, n = ctypes.c_float(0), ctypes.c_int(0)
+        _lib.check(L.gf_profile_field_ms(handle, ctypes.byref(tot), ctypes.byref(n)))
+        field_ms.append(tot.value)
+    _lib.check(L.gf_profile_enable(handle, 0))
+    field_ms_per_frame = float(np.median(field_ms))
+
+    t = torch.tensor([ms_res, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_res, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    value = world * args.steps / (ms_res / 1000.0)
+    e2e = world * args.steps / (ms_e2e / 1000.0)
+    achieved = samples_per_frame * HEAD_SAMPLE_BYTES / (field_ms_per_frame / 1000.0) / 1e9
+    tflops = samples_per_frame * HEAD_SAMPLE_FLOP / (field_ms_per_frame / 1000.0) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic",
+        "config": {"workload": "RAD-NeRF head+torso (May cfg architecture), 512x512 rays x 128 samples = 33,554,432 field evaluations/frame "
+                               "(bound=4, 3 cascades, all-ones bitfield, dt_gamma=0, max_steps=128) + torso field on the lower image half",
+                   "frames_per_rank": args.steps, "sharding": "frames, rank-block; one NCCL parameter broadcast (%d B), no per-frame communication" % bcast_bytes,
+                   "l2": "per-round sample lists (335 MB) exceed L2; the 16 MB grid tables are the algorithm's own hot set; no explicit flush",
+                   "precision": args.precision, "samples_per_frame": samples_per_frame, "torso_pixels": torso_px, "s_total": s_total},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(conds_h[0].numel() * 4 + 16 * 4 + 6 * 4),
+                "d2h_bytes_per_step": int(host_rgb8.numel())},
+        "gpu_launches": launches * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                     "kernel": "k_field_tc" if args.precision == "fp16" else "k_field_fp32", "kernel_ms_per_frame": field_ms_per_frame,
+                     "kernel_share_of_step": field_ms_per_frame / (ms_res / args.steps), "peak_source": peaks["source"],
+                     "tensor_tflops": tflops, "tensor_frac_of_bf16_peak": tflops / peaks["bf16_tflops"],
+                     "note": "algorithmic gather bytes (1536 B/sample); the 16 MB tables are L2-resident so DRAM traffic is far below this"},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        fps, dt, threads, sample = cpu_port_fps(2048)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample}
+    if not args.no_ref_cuda and world == 1:
+        try:
+            line["reference_cuda"] = reference_cuda_fps(model, hp, fi, dev)
+        except Exception as e:  # noqa: BLE001
+            line["reference_cuda"] = {"unavailable": repr(e)[:200]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_cuda_fps(model, hp, fi, dev):
+    """Context number: the reference renderer assembled from the compiled UNMODIFIED reference kernels (oracle/_ref) on the
+    same GPU and workload (the 'kernel to beat', BASELINE.md B-REF-CUDA).  Not part of the product path."""
+    import torch
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        return {"unavailable": "oracle/_ref not built"}
+    from geneface_b200 import utils
+    ref = ref_gpu.RefRenderer(model.state_dict(), hp, torso=True)
+    rays = utils.get_rays(fi['pose'], fi['intrinsics'], H, W)
+    bgc = utils.get_bg_coords(H, W, dev)
+    times = []
+    with torch.no_grad():
+        cf = model.cal_cond_feat(fi['cond'])
+        for it in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ws, depth, img, nears, fars, _ = ref.render_head(rays['rays_o'][0], rays['rays_d'][0], cf, 0.0, MAX_STEPS)
+            bg, _, _ = ref.torso_bg(bgc[0], fi['poses6'], fi['bg_color'][0])
+            ref.finish(img, ws, depth, nears, fars, bg)
+            e1.record()
+            torch.cuda.synchronize()
+            if it:
+                times.append(e0.elapsed_time(e1))
+    ms = sorted(times)[len(times) // 2]
+    return {"value": 1000.0 / ms, "unit": "frames/s", "ms_per_frame": ms, "what": "reference host loop on its own compiled kernels + torch fp32 GEMMs, same frame"}
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,8 @@ _SIGS = {
     "gf_render_frame": [c_vp, c_vp, c_vp, c_vp, c_u64, c_vp],
     "gf_field_forward": [c_vp, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_u32, c_vp],
     "gf_tc_debug": [c_vp, c_vp],
+    "gf_profile_enable": [c_vp, c_int],
+    "gf_profile_field_ms": [c_vp, c_vp, c_vp],
     "gf_last_error": [],
     "gf_version": [],
     "gf_device_ok": [],

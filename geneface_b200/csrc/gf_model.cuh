@@ -108,6 +108,8 @@ struct FieldTcIO {
 
 }  // namespace gf
 
+#define GF_MAX_PROFILE_EVENTS 96
+
 // Opaque handle of the C ABI.
 struct GfModel {
     GfModelDesc desc;
@@ -119,4 +121,6 @@ struct GfModel {
     size_t tc_bytes;
     float* tc_dbg;          // diagnostics buffer for the tcgen05 kernel (gf_tc_debug) or null
     int num_sms;
+    int profiling, ev_used;
+    cudaEvent_t ev[GF_MAX_PROFILE_EVENTS];
 };

@@ -753,7 +753,34 @@ GF_API void gf_model_destroy(GfModel* m) {
     if (!m) return;
     if (m->w) cudaFree(m->w);
     if (m->tc_blob) cudaFree(m->tc_blob);
+    if (m->scratch_bias) cudaFree(m->scratch_bias);
+    for (int i = 0; i < GF_MAX_PROFILE_EVENTS; i++)
+        if (m->ev[i]) cudaEventDestroy(m->ev[i]);
     delete m;
+}
+
+GF_API int gf_profile_enable(GfModel* m, int enable) {
+    if (!m) return GF_ERR_INVALID;
+    m->profiling = enable != 0;
+    m->ev_used = 0;
+    return GF_OK;
+}
+
+// Sum of the CUDA-event durations (ms) of the field launches of the LAST gf_render_frame call; the caller must have
+// synchronised the stream.  *n_launches receives the number of bracketed launches.
+GF_API int gf_profile_field_ms(GfModel* m, float* total_ms, int* n_launches) {
+    if (!m || !total_ms) return GF_ERR_INVALID;
+    float tot = 0.f;
+    int n = 0;
+    for (int i = 0; i + 1 < m->ev_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, m->ev[i], m->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); set_error("profile: events not complete"); return GF_ERR_CUDA; }
+        tot += ms;
+        n++;
+    }
+    *total_ms = tot;
+    if (n_launches) *n_launches = n;
+    return GF_OK;
 }
 
 GF_API uint64_t gf_model_packed_bytes(const GfModel* m) { return m ? (uint64_t)m->w_floats * sizeof(float) : 0; }
@@ -845,7 +872,9 @@ GF_API int gf_render_frame(const GfModel* model, const GfFrame* f, const GfOut* 
     ca.N = N; ca.T_thresh = f->T_thresh; ca.max_steps = f->max_steps;
 
     const uint32_t chunk = RENDER_CHUNK_MAX;
-    auto field = [&](void) -> int {
+    GfModel* prof = model->profiling ? const_cast<GfModel*>(model) : nullptr;
+    if (prof) prof->ev_used = 0;
+    auto field_inner = [&](void) -> int {
         if (f->precision == 0) {
             FieldIO io;
             memset(&io, 0, sizeof(io));
@@ -859,6 +888,20 @@ GF_API int gf_render_frame(const GfModel* model, const GfFrame* f, const GfOut* 
         io.pos4 = w.sb.pos4; io.rays_d = w.st.rays_d; io.M_dev = w.ctl + CTL_TOTAL; io.out4 = w.sb.out4; io.bias_amb = w.bias_amb;
         io.stat_samples = w.stat;
         return field_tc_launch(model, io, st);
+    };
+    // optional CUDA-event bracket around every field launch (gf_profile_*): the dominant-kernel timing bench.py reports
+    auto field = [&](void) -> int {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (prof && prof->ev_used + 2 <= GF_MAX_PROFILE_EVENTS) {
+            for (int k = 0; k < 2; k++)
+                if (!prof->ev[prof->ev_used + k]) cudaEventCreate(&prof->ev[prof->ev_used + k]);
+            e0 = prof->ev[prof->ev_used]; e1 = prof->ev[prof->ev_used + 1];
+            prof->ev_used += 2;
+            cudaEventRecord(e0, st);
+        }
+        const int r = field_inner();
+        if (e1) cudaEventRecord(e1, st);
+        return r;
     };
 
     // pass A: rounds covering exactly max_steps slots

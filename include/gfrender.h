@@ -217,6 +217,11 @@ typedef struct GfOut {
 GF_API int gf_field_forward(const GfModel* model, const float* xyzs, const float* dirs, const float* cond_feat, uint32_t M,
                             float* sigmas, float* rgbs, float* ambient, uint32_t precision, gf_stream_t stream);
 
+/* Profiling: when enabled, gf_render_frame brackets every field-kernel launch with CUDA events on the launching
+ * stream; after synchronising, gf_profile_field_ms returns their summed duration for the last frame. */
+GF_API int gf_profile_enable(GfModel* model, int enable);
+GF_API int gf_profile_field_ms(GfModel* model, float* total_ms, int* n_launches);
+
 /* Diagnostics for the tcgen05 field kernel: when dbg != NULL the next precision-1 launches dump the fp32
  * accumulators of sample tile 0 after each MMA stage into dbg (device float[9*128*144]). */
 GF_API int gf_tc_debug(GfModel* model, float* dbg);

@@ -49,10 +49,15 @@ def grid_encode(x, bound, embeddings, offsets, per_level_scale, base_resolution=
 
 
 # ------------------------------------------------------------------ dense helpers
+# float64 accumulation for parity checks; bench.py's CPU-baseline leg switches to float32 (what the reference's
+# CPU tensors would use) so that the timing is not penalised by the checker's extra precision.
+MATMUL_DTYPE = np.float64
+
+
 def linear(x, W, b=None):
-    y = x.astype(np.float64) @ W.astype(np.float64).T
+    y = x.astype(MATMUL_DTYPE) @ W.astype(MATMUL_DTYPE).T
     if b is not None:
-        y = y + b.astype(np.float64)
+        y = y + b.astype(MATMUL_DTYPE)
     return y.astype(np.float32)
 
 
