@@ -354,11 +354,12 @@ class NeRFRenderer(nn.Module):
         if not use_loop:
             out = self.render_fused(cond_feat.detach(), 1, N, rays_o=rays_o, rays_d=rays_d, bg_color=bg_color, dt_gamma=dt_gamma,
                                     max_steps=max_steps, T_thresh=T_thresh, precision=kwargs.get('precision'),
-                                    want=('weights_sum', 'n_samples', 'counters'))
+                                    want=('weights_sum', 'n_samples', 'counters', 'term_hist'))
             results['depth_map'] = out['depth_map'].view(*prefix)
             results['rgb_map'] = out['rgb_map'].view(*prefix, 3)
             results['weights_sum_eval'] = out['weights_sum']
             results['n_samples'] = out['n_samples']
+            results['term_hist'] = out['term_hist']
             self.last_counters = out['counters']
             return results
         nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer, self.min_near)
@@ -584,13 +585,14 @@ class RADNeRFTorso(RADNeRF):
             out = self.render_fused(cond_feat, 1, N, rays_o=rays_o, rays_d=rays_d, bg_color=bg_color, bg_coords=bg_coords,
                                     torso_pose=poses, dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh,
                                     precision=kwargs.get('precision'),
-                                    want=('weights_sum', 'torso_alpha_map', 'torso_rgb_map', 'n_samples', 'counters'))
+                                    want=('weights_sum', 'torso_alpha_map', 'torso_rgb_map', 'n_samples', 'counters', 'term_hist'))
             results['torso_alpha_map'] = out['torso_alpha_map'].view(N, 1)
             results['torso_rgb_map'] = out['torso_rgb_map'].view(1, N, 3) if len(prefix) == 2 else out['torso_rgb_map']
             results['depth_map'] = out['depth_map'].view(*prefix)
             results['rgb_map'] = out['rgb_map'].view(*prefix, 3)
             results['weights_sum_eval'] = out['weights_sum']
             results['n_samples'] = out['n_samples']
+            results['term_hist'] = out['term_hist']
             self.last_counters = out['counters']
             return results
         # ---- reference structure (radnerf_torso.py:92-196) on our ops ----

@@ -229,3 +229,18 @@ def test_render_loop_schedule_bounds():
     assert hp['max_steps'] <= s_total <= hp['max_steps'] + 7
     assert ns.max() <= s_total and (ws >= 0).all() and (ws <= 1 + 1e-5).all()
     assert trace[0] == (400, 1)
+
+
+def test_golden_adnerf_port(golden_dir):
+    """The vanilla AD-NeRF port (CPU baseline of BASELINE.json configs[0]) against outputs of the reference's own
+    modules/nerfs code imported in the build container (oracle/gen_golden_adnerf.py)."""
+    import torch
+    from oracle import adnerf_port
+    g = golden(golden_dir, "adnerf.npz")
+    sd = adnerf_port.init_state(seed=0)
+    cond = torch.randn(8, 16, 29, generator=torch.Generator().manual_seed(1))
+    assert np.allclose(adnerf_port.cal_cond_feat(sd, cond).numpy(), g["cond_feat"], atol=1e-6)
+    rgb, acc, last_w = adnerf_port.render_frame(sd, 16, 16)
+    assert np.allclose(rgb.numpy(), g["rgb"], atol=2e-5) and np.allclose(acc.numpy(), g["acc"], atol=2e-5)
+    assert np.allclose(last_w.numpy(), g["last_weight"], atol=2e-5)
+    assert g["rgb"].std() > 1e-4          # the fixture is not a constant image
