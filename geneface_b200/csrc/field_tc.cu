@@ -286,16 +286,14 @@ __global__ void __launch_bounds__(256, 1) k_field_tc(const TcArgs a) {
         }
         // ---- 3D grid: 16 levels x 8 corners -> 32 fp16 features in F[row][k 0..31] ---------------------
         {
-            const float ux = to_unit(x, a.bound), uy = to_unit(y, a.bound), uz = to_unit(z, a.bound);
+            // invalid rows sample an out-of-range point (-> zeros, no loads)
+            const float ux = valid ? to_unit(x, a.bound) : -1.f, uy = to_unit(y, a.bound), uz = to_unit(z, a.bound);
             #pragma unroll
-            for (int u = 0; u < 4; u++) {                       // 16-byte unit u holds levels 4u..4u+3
-                uint32_t p[4];
-                #pragma unroll
-                for (int l = 0; l < 4; l++) {
-                    const float2 f = valid ? grid3_sample(a.pos, 4 * u + l, ux, uy, uz) : make_float2(0.f, 0.f);
-                    p[l] = pack_h2(f.x, f.y);
-                }
-                *reinterpret_cast<uint4*>(F + sw128(row, u)) = make_uint4(p[0], p[1], p[2], p[3]);
+            for (int u = 0; u < 4; u++) {                       // 16-byte unit u holds levels 4u..4u+3; 32 gathers in flight
+                float2 f[4];
+                grid3_levels<4>(a.pos, 4 * u, ux, uy, uz, f);
+                *reinterpret_cast<uint4*>(F + sw128(row, u)) =
+                    make_uint4(pack_h2(f[0].x, f[0].y), pack_h2(f[1].x, f[1].y), pack_h2(f[2].x, f[2].y), pack_h2(f[3].x, f[3].y));
             }
         }
         fence_async_smem();
@@ -342,16 +340,16 @@ __global__ void __launch_bounds__(256, 1) k_field_tc(const TcArgs a) {
         const float ax = tanhf(amb[0]), ay = tanhf(amb[1]);
         // ---- 2D ambient grid -> F[row][k 32..63] ------------------------------------------------------------
         {
-            const float vx = to_unit(ax, 1.0f), vy = to_unit(ay, 1.0f);
+            const float vx = valid ? to_unit(ax, 1.0f) : -1.f, vy = to_unit(ay, 1.0f);
             #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                uint32_t p[4];
+            for (int hb = 0; hb < 2; hb++) {                    // 8 levels = 32 gathers in flight
+                float2 f[8];
+                grid2_levels<8>(a.amb, 8 * hb, vx, vy, f);
                 #pragma unroll
-                for (int l = 0; l < 4; l++) {
-                    const float2 f = valid ? grid2_sample(a.amb, 4 * u + l, vx, vy) : make_float2(0.f, 0.f);
-                    p[l] = pack_h2(f.x, f.y);
-                }
-                *reinterpret_cast<uint4*>(F + sw128(row, 4 + u)) = make_uint4(p[0], p[1], p[2], p[3]);
+                for (int u = 0; u < 2; u++)
+                    *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * hb + u)) =
+                        make_uint4(pack_h2(f[4 * u].x, f[4 * u].y), pack_h2(f[4 * u + 1].x, f[4 * u + 1].y),
+                                   pack_h2(f[4 * u + 2].x, f[4 * u + 2].y), pack_h2(f[4 * u + 3].x, f[4 * u + 3].y));
             }
         }
         fence_async_smem();

@@ -7,11 +7,20 @@
 namespace gf {
 
 // ---- per-level geometry, computed ON DEVICE once per model (exp2f must be the GPU's) ----------
+// The reference recomputes `get_grid_index` (3 conditional stride steps + a runtime modulo) for every
+// corner (gridencoder.cu:66-84).  Both are level constants: which dimensions enter the index
+// (stride <= hashmap_size), and the modulo, which is a no-op on dense levels (index < hsize) and a
+// power-of-two mask on clipped/hashed levels (hsize == 2^log2_hashmap_size).  k_level_geometry
+// derives sy/sz/mask/hashed once; the integer results are identical to the reference's.
 struct GridLevels {
     float scale[16];
     uint32_t res[16];      // resolution = ceil(scale)+1
     uint32_t hsize[16];    // entries in the level
     uint32_t offset[16];   // first entry of the level
+    uint32_t sy[16];       // stride of y in the index (0 when dropped)
+    uint32_t sz[16];       // stride of z (0 when dropped; unused for 2-D grids)
+    uint32_t mask[16];     // index & mask  ==  index % hsize
+    uint32_t hashed[16];   // 1: fast_hash index (gridtype 0 on a clipped level)
 };
 
 struct GridDesc {
@@ -21,75 +30,124 @@ struct GridDesc {
     uint32_t interp;       // 0 linear, 1 smoothstep
 };
 
-__device__ __forceinline__ uint32_t grid_index3(uint32_t gridtype, uint32_t hs, uint32_t res, uint32_t x, uint32_t y, uint32_t z) {
-    // gridencoder.cu:66-84 with D=3, align_corners=false
-    uint32_t stride = 1, index = 0;
-    const uint32_t r1 = res + 1;
-    if (stride <= hs) { index += x * stride; stride *= r1; }
-    if (stride <= hs) { index += y * stride; stride *= r1; }
-    if (stride <= hs) { index += z * stride; stride *= r1; }
-    if (gridtype == 0 && stride > hs) index = (x * 1u) ^ (y * 2654435761u) ^ (z * 805459861u);
-    return index % hs;
-}
-
-__device__ __forceinline__ uint32_t grid_index2(uint32_t gridtype, uint32_t hs, uint32_t res, uint32_t x, uint32_t y) {
-    uint32_t stride = 1, index = 0;
-    const uint32_t r1 = res + 1;
-    if (stride <= hs) { index += x * stride; stride *= r1; }
-    if (stride <= hs) { index += y * stride; stride *= r1; }
-    if (gridtype == 0 && stride > hs) index = (x * 1u) ^ (y * 2654435761u);
-    return index % hs;
-}
-
 __device__ __forceinline__ float smooth_(float v) { return v * v * (3.0f - 2.0f * v); }
 
-// x,y,z already mapped to [0,1] (grid.py:149).  Returns the 2 interpolated channels of `level`.
-__device__ __forceinline__ float2 grid3_sample(const GridDesc& g, int level, float x, float y, float z) {
-    if (x < 0 || x > 1 || y < 0 || y > 1 || z < 0 || z > 1) return make_float2(0.f, 0.f);
-    const float scale = g.lv.scale[level];
-    const uint32_t res = g.lv.res[level], hs = g.lv.hsize[level];
-    const float2* __restrict__ tab = g.table + g.lv.offset[level];
-    float px = __fmaf_rn(x, scale, 0.5f), py = __fmaf_rn(y, scale, 0.5f), pz = __fmaf_rn(z, scale, 0.5f);
-    const uint32_t gx = (uint32_t)floorf(px), gy = (uint32_t)floorf(py), gz = (uint32_t)floorf(pz);
-    px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy); pz = __fsub_rn(pz, (float)gz);
-    if (g.interp == 1) { px = smooth_(px); py = smooth_(py); pz = smooth_(pz); }
-    const float qx = __fsub_rn(1.0f, px), qy = __fsub_rn(1.0f, py), qz = __fsub_rn(1.0f, pz);
-    float2 v[8];
-    #pragma unroll
-    for (int i = 0; i < 8; i++)
-        v[i] = __ldg(tab + grid_index3(g.gridtype, hs, res, gx + (i & 1), gy + ((i >> 1) & 1), gz + (i >> 2)));
-    float r0 = 0.f, r1 = 0.f;
-    #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        // w = ((1 * wx) * wy) * wz in the reference's order (d = 0,1,2)
-        const float w = __fmul_rn(__fmul_rn((i & 1) ? px : qx, ((i >> 1) & 1) ? py : qy), (i >> 2) ? pz : qz);
-        r0 = __fmaf_rn(w, v[i].x, r0);
-        r1 = __fmaf_rn(w, v[i].y, r1);
+constexpr uint32_t HASH_P1 = 2654435761u, HASH_P2 = 805459861u;   // gridencoder.cu:54
+
+// indices of the 8 corners of level `l` around integer cell (gx,gy,gz)
+__device__ __forceinline__ void corner_index3(const GridLevels& lv, int l, uint32_t gx, uint32_t gy, uint32_t gz, uint32_t (&idx)[8]) {
+    const uint32_t mask = lv.mask[l];
+    if (lv.hashed[l]) {
+        const uint32_t hx[2] = {gx, gx + 1}, hy[2] = {gy * HASH_P1, (gy + 1) * HASH_P1}, hz[2] = {gz * HASH_P2, (gz + 1) * HASH_P2};
+        #pragma unroll
+        for (int c = 0; c < 8; c++) idx[c] = (hx[c & 1] ^ hy[(c >> 1) & 1] ^ hz[c >> 2]) & mask;
+    } else {
+        const uint32_t sy = lv.sy[l], sz = lv.sz[l];
+        const uint32_t b = gx + gy * sy + gz * sz;
+        #pragma unroll
+        for (int c = 0; c < 8; c++) idx[c] = (b + (c & 1) + ((c >> 1) & 1) * sy + (c >> 2) * sz) & mask;
     }
-    return make_float2(r0, r1);
 }
 
-__device__ __forceinline__ float2 grid2_sample(const GridDesc& g, int level, float x, float y) {
-    if (x < 0 || x > 1 || y < 0 || y > 1) return make_float2(0.f, 0.f);
-    const float scale = g.lv.scale[level];
-    const uint32_t res = g.lv.res[level], hs = g.lv.hsize[level];
-    const float2* __restrict__ tab = g.table + g.lv.offset[level];
-    float px = __fmaf_rn(x, scale, 0.5f), py = __fmaf_rn(y, scale, 0.5f);
-    const uint32_t gx = (uint32_t)floorf(px), gy = (uint32_t)floorf(py);
-    px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy);
-    if (g.interp == 1) { px = smooth_(px); py = smooth_(py); }
-    const float qx = __fsub_rn(1.0f, px), qy = __fsub_rn(1.0f, py);
-    float2 v[4];
-    #pragma unroll
-    for (int i = 0; i < 4; i++) v[i] = __ldg(tab + grid_index2(g.gridtype, hs, res, gx + (i & 1), gy + (i >> 1)));
-    float r0 = 0.f, r1 = 0.f;
-    #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const float w = __fmul_rn((i & 1) ? px : qx, (i >> 1) ? py : qy);
-        r0 = __fmaf_rn(w, v[i].x, r0);
-        r1 = __fmaf_rn(w, v[i].y, r1);
+__device__ __forceinline__ void corner_index2(const GridLevels& lv, int l, uint32_t gx, uint32_t gy, uint32_t (&idx)[4]) {
+    const uint32_t mask = lv.mask[l];
+    if (lv.hashed[l]) {
+        const uint32_t hx[2] = {gx, gx + 1}, hy[2] = {gy * HASH_P1, (gy + 1) * HASH_P1};
+        #pragma unroll
+        for (int c = 0; c < 4; c++) idx[c] = (hx[c & 1] ^ hy[c >> 1]) & mask;
+    } else {
+        const uint32_t sy = lv.sy[l];
+        const uint32_t b = gx + gy * sy;
+        #pragma unroll
+        for (int c = 0; c < 4; c++) idx[c] = (b + (c & 1) + (c >> 1) * sy) & mask;
     }
-    return make_float2(r0, r1);
+}
+
+// NL consecutive levels of the 3-D grid with ALL 8*NL corner loads issued before any is consumed
+// (memory-level parallelism: the gathers are L2-latency bound).  x,y,z already mapped to [0,1]
+// (grid.py:149).  Interpolation arithmetic and accumulation order are the reference's (bit-identical
+// to k_grid_forward).  out[i] = the 2 channels of level l0+i.
+template <int NL>
+__device__ __forceinline__ void grid3_levels(const GridDesc& g, int l0, float x, float y, float z, float2 (&out)[NL]) {
+    const bool oob = x < 0 || x > 1 || y < 0 || y > 1 || z < 0 || z > 1;
+    float fx[NL], fy[NL], fz[NL];
+    float2 v[NL][8];
+    #pragma unroll
+    for (int i = 0; i < NL; i++) {
+        const int l = l0 + i;
+        const float scale = g.lv.scale[l];
+        float px = __fmaf_rn(x, scale, 0.5f), py = __fmaf_rn(y, scale, 0.5f), pz = __fmaf_rn(z, scale, 0.5f);
+        const uint32_t gx = (uint32_t)floorf(px), gy = (uint32_t)floorf(py), gz = (uint32_t)floorf(pz);
+        px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy); pz = __fsub_rn(pz, (float)gz);
+        if (g.interp == 1) { px = smooth_(px); py = smooth_(py); pz = smooth_(pz); }
+        fx[i] = px; fy[i] = py; fz[i] = pz;
+        uint32_t idx[8];
+        corner_index3(g.lv, l, gx, gy, gz, idx);
+        const float2* __restrict__ tab = g.table + g.lv.offset[l];
+        #pragma unroll
+        for (int c = 0; c < 8; c++) v[i][c] = oob ? make_float2(0.f, 0.f) : __ldg(tab + idx[c]);
+    }
+    #pragma unroll
+    for (int i = 0; i < NL; i++) {
+        const float px = fx[i], py = fy[i], pz = fz[i];
+        const float qx = __fsub_rn(1.0f, px), qy = __fsub_rn(1.0f, py), qz = __fsub_rn(1.0f, pz);
+        float r0 = 0.f, r1 = 0.f;
+        #pragma unroll
+        for (int c = 0; c < 8; c++) {
+            // w = ((1 * wx) * wy) * wz in the reference's order (d = 0,1,2)
+            const float w = __fmul_rn(__fmul_rn((c & 1) ? px : qx, ((c >> 1) & 1) ? py : qy), (c >> 2) ? pz : qz);
+            r0 = __fmaf_rn(w, v[i][c].x, r0);
+            r1 = __fmaf_rn(w, v[i][c].y, r1);
+        }
+        out[i] = make_float2(r0, r1);
+    }
+}
+
+template <int NL>
+__device__ __forceinline__ void grid2_levels(const GridDesc& g, int l0, float x, float y, float2 (&out)[NL]) {
+    const bool oob = x < 0 || x > 1 || y < 0 || y > 1;
+    float fx[NL], fy[NL];
+    float2 v[NL][4];
+    #pragma unroll
+    for (int i = 0; i < NL; i++) {
+        const int l = l0 + i;
+        const float scale = g.lv.scale[l];
+        float px = __fmaf_rn(x, scale, 0.5f), py = __fmaf_rn(y, scale, 0.5f);
+        const uint32_t gx = (uint32_t)floorf(px), gy = (uint32_t)floorf(py);
+        px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy);
+        if (g.interp == 1) { px = smooth_(px); py = smooth_(py); }
+        fx[i] = px; fy[i] = py;
+        uint32_t idx[4];
+        corner_index2(g.lv, l, gx, gy, idx);
+        const float2* __restrict__ tab = g.table + g.lv.offset[l];
+        #pragma unroll
+        for (int c = 0; c < 4; c++) v[i][c] = oob ? make_float2(0.f, 0.f) : __ldg(tab + idx[c]);
+    }
+    #pragma unroll
+    for (int i = 0; i < NL; i++) {
+        const float px = fx[i], py = fy[i];
+        const float qx = __fsub_rn(1.0f, px), qy = __fsub_rn(1.0f, py);
+        float r0 = 0.f, r1 = 0.f;
+        #pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float w = __fmul_rn((c & 1) ? px : qx, (c >> 1) ? py : qy);
+            r0 = __fmaf_rn(w, v[i][c].x, r0);
+            r1 = __fmaf_rn(w, v[i][c].y, r1);
+        }
+        out[i] = make_float2(r0, r1);
+    }
+}
+
+// single-level conveniences (fp32 SIMT kernels: one (sample, level) task per thread)
+__device__ __forceinline__ float2 grid3_sample(const GridDesc& g, int level, float x, float y, float z) {
+    float2 o[1];
+    grid3_levels<1>(g, level, x, y, z, o);
+    return o[0];
+}
+__device__ __forceinline__ float2 grid2_sample(const GridDesc& g, int level, float x, float y) {
+    float2 o[1];
+    grid2_levels<1>(g, level, x, y, o);
+    return o[0];
 }
 
 // map a world coordinate in [-bound, bound] to [0,1] exactly as grid.py:149 does in fp32

@@ -37,15 +37,35 @@ namespace gf {
 // ======================================================================================
 // model setup kernels
 // ======================================================================================
-__global__ void k_level_geometry(const int* __restrict__ offsets, float S, uint32_t H, GridLevels* out) {
+__global__ void k_level_geometry(const int* __restrict__ offsets, float S, uint32_t H, uint32_t D, uint32_t gridtype, GridLevels* out,
+                                 int* __restrict__ bad) {
     const int l = threadIdx.x;
     if (l >= 16) return;
     // gridencoder.cu:137-139 (device exp2f on purpose: bit-identical scale to the reference kernel)
     const float scale = __fmaf_rn(exp2f(__fmul_rn((float)l, S)), (float)H, -1.0f);
+    const uint32_t res = (uint32_t)ceilf(scale) + 1;
+    const uint32_t hs = (uint32_t)(offsets[l + 1] - offsets[l]);
     out->scale[l] = scale;
-    out->res[l] = (uint32_t)ceilf(scale) + 1;
-    out->hsize[l] = (uint32_t)(offsets[l + 1] - offsets[l]);
+    out->res[l] = res;
+    out->hsize[l] = hs;
     out->offset[l] = (uint32_t)offsets[l];
+    // replay of the stride loop of get_grid_index (gridencoder.cu:68-75, align_corners = false), uint32 wrap-around included
+    const uint32_t R = res + 1;
+    uint32_t stride = 1, sy = 0, sz = 0;
+    stride *= R;                                              // d = 0 is always taken (1 <= hashmap_size)
+    if (stride <= hs) { sy = stride; stride *= R; }
+    if (D == 3 && stride <= hs) { sz = stride; stride *= R; }
+    out->sy[l] = sy;
+    out->sz[l] = sz;
+    out->hashed[l] = (gridtype == 0 && stride > hs) ? 1u : 0u;
+    const bool pow2 = hs && (hs & (hs - 1)) == 0;
+    out->mask[l] = pow2 ? hs - 1 : 0xFFFFFFFFu;
+    // `index % hsize` is only replaced by the mask when it is provably the same: power-of-two level, or a dense level
+    // whose largest reachable index (pos_grid <= res per axis) stays below hsize.
+    if (!pow2) {
+        const unsigned long long maxidx = (unsigned long long)res * (1ull + sy + sz);
+        if (out->hashed[l] || maxidx >= hs) *bad = 1;
+    }
 }
 
 // dst[k][n] = src[n][k0 + k]   (src row-major [N][ldsrc]); dst row stride ldd
@@ -720,15 +740,25 @@ GF_API int gf_model_create(const GfModelDesc* d, GfModel** out, gf_stream_t stre
     }
     // ---- level geometry on device ----
     GridLevels* lv_dev = nullptr;
-    cudaMalloc(&lv_dev, 3 * sizeof(GridLevels));
-    k_level_geometry<<<1, 32, 0, st>>>(d->pos_offsets, d->pos_S, d->pos_H, lv_dev + 0);
-    k_level_geometry<<<1, 32, 0, st>>>(d->amb_offsets, d->amb_S, d->amb_H, lv_dev + 1);
-    if (d->has_torso) k_level_geometry<<<1, 32, 0, st>>>(d->torso_offsets, d->torso_S, d->torso_H, lv_dev + 2);
+    cudaMalloc(&lv_dev, 3 * sizeof(GridLevels) + 16);
+    int* bad_dev = reinterpret_cast<int*>(lv_dev + 3);
+    cudaMemsetAsync(lv_dev, 0, 3 * sizeof(GridLevels) + 16, st);
+    k_level_geometry<<<1, 32, 0, st>>>(d->pos_offsets, d->pos_S, d->pos_H, 3, d->gridtype, lv_dev + 0, bad_dev);
+    k_level_geometry<<<1, 32, 0, st>>>(d->amb_offsets, d->amb_S, d->amb_H, 2, d->gridtype, lv_dev + 1, bad_dev);
+    if (d->has_torso) k_level_geometry<<<1, 32, 0, st>>>(d->torso_offsets, d->torso_S, d->torso_H, 2, 1, lv_dev + 2, bad_dev);
     GridLevels lv_host[3];
+    int bad_host = 0;
     memset(lv_host, 0, sizeof(lv_host));
     cudaMemcpyAsync(lv_host, lv_dev, 3 * sizeof(GridLevels), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&bad_host, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(lv_dev);
+    if (e == cudaSuccess && bad_host) {
+        set_error("model_create: a grid level is neither dense nor a power of two in size (offsets not produced by GridEncoder?)");
+        cudaFree(w);
+        delete m;
+        return GF_ERR_UNSUPPORTED;
+    }
     if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
         set_error("model_create: %s", cudaGetErrorString(e));
         cudaFree(w);
