@@ -409,7 +409,7 @@ def test_fused_frame_vs_compiled_reference_renderer(torso, bitfield, sigma_scale
     assert_close(res['rgb_map'][0].cpu().numpy(), img_r.cpu().numpy(), what="rgb_map (render())")
     assert_close(res['depth_map'][0].cpu().numpy(), depth_r.cpu().numpy(), what="depth_map (render())")
     assert_close(res['weights_sum_eval'].cpu().numpy(), ws.cpu().numpy(), what="weights_sum (render())")
-    if bitfield == 'S':     # in-kernel ray generation differs from torch's get_rays by <= 1 ulp: only meaningful on a smooth occupancy
+    if bitfield == 'S' and sigma_scale <= 4:     # in-kernel ray generation differs from torch's get_rays by <= 1 ulp: only meaningful on a smooth occupancy
         assert_close(out['rgb_map'].cpu().numpy(), img_r.cpu().numpy(), what="rgb_map (in-kernel rays)")
         assert_close(out['weights_sum'].cpu().numpy(), ws.cpu().numpy(), what="weights_sum (in-kernel rays)")
     if torso:
@@ -493,15 +493,16 @@ def test_tc_field_every_mma_stage_matches_fp16_emulation(head_model):
     bias_ind = Wc[0][:, 144:] @ sd['individual_embeddings'][0].astype(np.float64)
     pos_feat = OF.grid_encode(xyz[:128], 1.0, sd['position_embedder.embeddings'], fo.pos_offsets, fo.pos_pls)
 
-    def check(stage, cols, expect, what):
+    def check(stage, cols, expect, what, rel=2e-3):
         got = D[stage][:, cols]
-        tol = 2e-3 * np.abs(expect).max() + 1e-3 * np.abs(expect)
+        tol = rel * np.abs(expect).max() + 0.5 * rel * np.abs(expect)
         bad = np.abs(got - expect) > tol
         assert not bad.any(), f"stage {stage} ({what}): {bad.sum()} of {bad.size} wrong, max err {np.abs(got - expect).max():.3e}, ref max {np.abs(expect).max():.3e}"
 
-    check(0, slice(0, 128), _h(pos_feat) @ _h(Wa[0][:, :32]).T, "ambient L0, SS K=32")
-    check(1, slice(0, 128), _h(relu(D[0][:, :128] + bias_cond)) @ _h(Wa[1]).T, "ambient L1, TS K=128")
-    check(2, slice(0, 2), _h(relu(D[1][:, :128])) @ _h(Wa[2]).T, "ambient L2, TS N=16")
+    # ambient branch: split (hi+lo) fp16 operands ~ 22 bits -> compare against the exact product at 5e-5
+    check(0, slice(0, 128), pos_feat.astype(np.float64) @ Wa[0][:, :32].T, "ambient L0, SS split K=64+32", rel=5e-4)   # oracle features differ by up to 2e-4 (libm vs GPU exp2f level scales)
+    check(1, slice(0, 128), relu(D[0][:, :128] + bias_cond) @ Wa[1].T, "ambient L1, TS split 3x K=128", rel=5e-5)
+    check(2, slice(0, 2), relu(D[1][:, :128]) @ Wa[2].T, "ambient L2, fp32 CUDA cores", rel=2e-5)
     amb_pos = np.tanh(D[2][:, :2]).astype(np.float32)
     assert_close(amb.cpu().numpy()[:128], amb_pos, rel=1e-5, abs_=1e-6, what="ambient_pos output")
     amb_feat = OF.grid_encode(amb_pos, 1, sd['ambient_embedder.embeddings'], fo.amb_offsets, fo.amb_pls)
