@@ -24,6 +24,8 @@
 // stream is in a gather/epilogue phase the tensor core works on the other stream's layer.
 #include <cuda_fp16.h>
 
+#include <cstring>
+
 #include "gf_model.cuh"
 
 namespace gf {
@@ -233,6 +235,33 @@ __device__ __forceinline__ void epilogue_relu_to_A(uint32_t t_d, uint32_t t_a, u
     tmem_wait_st();
 }
 
+// 3-D grid, levels 8*HALF .. 8*HALF+7 of one row: fp16 hi into F[row][k 16*HALF ..], fp16 residual into F[row][k 32+16*HALF ..]
+template <int HALF>
+__device__ __forceinline__ void gather3_half(const GridDesc& g, float ux, float uy, float uz, uint8_t* F, uint32_t row) {
+    #pragma unroll
+    for (int b = 0; b < 2; b++) {                       // 4 levels per batch: up to 32 gathers in flight
+        float2 f[4];
+        grid3_levels<4, true>(g, 8 * HALF + 4 * b, ux, uy, uz, f);
+        *reinterpret_cast<uint4*>(F + sw128(row, 2 * HALF + b)) =
+            make_uint4(pack_h2(f[0].x, f[0].y), pack_h2(f[1].x, f[1].y), pack_h2(f[2].x, f[2].y), pack_h2(f[3].x, f[3].y));
+        *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * HALF + b)) =
+            make_uint4(pack_h2(h_resid(f[0].x), h_resid(f[0].y)), pack_h2(h_resid(f[1].x), h_resid(f[1].y)),
+                       pack_h2(h_resid(f[2].x), h_resid(f[2].y)), pack_h2(h_resid(f[3].x), h_resid(f[3].y)));
+    }
+}
+
+// 2-D ambient grid, levels 8*HALF .. 8*HALF+7 -> F[row][k 32+16*HALF ..]
+template <int HALF>
+__device__ __forceinline__ void gather2_half(const GridDesc& g, float vx, float vy, uint8_t* F, uint32_t row) {
+    float2 f[8];
+    grid2_levels<8>(g, 8 * HALF, vx, vy, f);                          // 32 gathers in flight
+    #pragma unroll
+    for (int u = 0; u < 2; u++)
+        *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * HALF + u)) =
+            make_uint4(pack_h2(f[4 * u].x, f[4 * u].y), pack_h2(f[4 * u + 1].x, f[4 * u + 1].y),
+                       pack_h2(f[4 * u + 2].x, f[4 * u + 2].y), pack_h2(f[4 * u + 3].x, f[4 * u + 3].y));
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
@@ -241,10 +270,32 @@ struct TcArgs {
     float bound;
     const uint8_t* wimg;        // WB_TOTAL bytes, global
     const float* bias_ind;      // [128] fp32 (packed fp32 blob, c_bind) or null
-    const float* w_amb2;        // [2][128] fp32 ambient output layer (packed fp32 blob, a_w2)
+    float w_amb2[256];          // [2][128] fp32 ambient output layer, by value: FFMA reads it straight from the constant bank
     FieldTcIO io;
     float* dbg;                 // [9][128][144] floats or null: accumulators of tile 0 after each layer
 };
+
+// ambient output layer (128 -> 2) over this thread's 64 accumulator columns, fp32, weights from the constant bank
+template <int HALF>
+__device__ __forceinline__ void amb2_partial(const TcArgs& a, uint32_t t_d, float* dbg, float& s0, float& s1) {
+    #pragma unroll
+    for (int c = 0; c < 2; c++) {
+        constexpr int base = 64 * HALF;
+        const int col = base + 32 * c;
+        float v[32];
+        tmem_ld32(t_d + col, v);
+        if (dbg) {
+            #pragma unroll
+            for (int j = 0; j < 32; j++) dbg[1 * 128 * 144 + col + j] = v[j];
+        }
+        #pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const float r = fmaxf(v[j], 0.f);
+            s0 = fmaf(r, a.w_amb2[base + 32 * c + j], s0);
+            s1 = fmaf(r, a.w_amb2[128 + base + 32 * c + j], s1);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_field_tc(const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -312,18 +363,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_field_tc(const TcArgs a) {
         }
         // ---- 3D grid: this thread takes levels 8*half .. 8*half+7 -> fp16 hi into F[row][k 16h..16h+15], residual into k 32+16h.. ------
         {
-            // invalid rows sample an out-of-range point (-> zeros, no loads)
-            const float ux = valid ? to_unit(x, a.bound) : -1.f, uy = to_unit(y, a.bound), uz = to_unit(z, a.bound);
-            #pragma unroll
-            for (int b = 0; b < 2; b++) {                       // 4 levels = 32 gathers in flight
-                float2 f[4];
-                grid3_levels<4>(a.pos, 8 * half + 4 * b, ux, uy, uz, f);
-                *reinterpret_cast<uint4*>(F + sw128(row, 2 * half + b)) =
-                    make_uint4(pack_h2(f[0].x, f[0].y), pack_h2(f[1].x, f[1].y), pack_h2(f[2].x, f[2].y), pack_h2(f[3].x, f[3].y));
-                *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * half + b)) =
-                    make_uint4(pack_h2(h_resid(f[0].x), h_resid(f[0].y)), pack_h2(h_resid(f[1].x), h_resid(f[1].y)),
-                               pack_h2(h_resid(f[2].x), h_resid(f[2].y)), pack_h2(h_resid(f[3].x), h_resid(f[3].y)));
-            }
+            // rows past the end of the list sample the centre (results are discarded)
+            const float ux = valid ? to_unit(x, a.bound) : 0.5f, uy = to_unit(y, a.bound), uz = to_unit(z, a.bound);
+            // `half` is warp-uniform: two copies of the code so that every per-level constant is an immediate constant-bank operand
+            if (half == 0) gather3_half<0>(a.pos, ux, uy, uz, F, row);
+            else gather3_half<1>(a.pos, ux, uy, uz, F, row);
         }
         fence_async_smem();
         tc_fence_before();
@@ -362,22 +406,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_field_tc(const TcArgs a) {
         float ax, ay;
         {
             float s0 = 0.f, s1 = 0.f;
-            #pragma unroll 1
-            for (int c = 0; c < 2; c++) {
-                const int col = 64 * half + 32 * c;
-                float v[32];
-                tmem_ld32(t_d + col, v);
-                if (dbg) {
-                    #pragma unroll
-                    for (int j = 0; j < 32; j++) dbg[1 * 128 * 144 + col + j] = v[j];
-                }
-                #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const float r = fmaxf(v[j], 0.f);
-                    s0 = fmaf(r, __ldg(a.w_amb2 + col + j), s0);
-                    s1 = fmaf(r, __ldg(a.w_amb2 + 128 + col + j), s1);
-                }
-            }
+            if (half == 0) amb2_partial<0>(a, t_d, dbg, s0, s1);
+            else amb2_partial<1>(a, t_d, dbg, s0, s1);
             xch[half * 128 + row] = make_float2(s0, s1);
             tc_fence_before();
             bar_stream(bar_id);
@@ -389,14 +419,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_field_tc(const TcArgs a) {
         }
         // ---- 2D ambient grid: levels 8*half .. +7 -> F[row][k 32+16h .. 32+16h+15] -------------------------------------------------------------------
         {
-            const float vx = valid ? to_unit(ax, 1.0f) : -1.f, vy = to_unit(ay, 1.0f);
-            float2 f[8];
-            grid2_levels<8>(a.amb, 8 * half, vx, vy, f);                  // 32 gathers in flight
-            #pragma unroll
-            for (int u = 0; u < 2; u++)
-                *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * half + u)) =
-                    make_uint4(pack_h2(f[4 * u].x, f[4 * u].y), pack_h2(f[4 * u + 1].x, f[4 * u + 1].y),
-                               pack_h2(f[4 * u + 2].x, f[4 * u + 2].y), pack_h2(f[4 * u + 3].x, f[4 * u + 3].y));
+            const float vx = to_unit(ax, 1.0f), vy = to_unit(ay, 1.0f);
+            if (half == 0) gather2_half<0>(a.amb, vx, vy, F, row);
+            else gather2_half<1>(a.amb, vx, vy, F, row);
         }
         fence_async_smem();
         tc_fence_before();
@@ -516,6 +541,14 @@ static int ensure_tc_pack(GfModel* m, cudaStream_t st) {
         set_error("tc pack: cannot reserve %u bytes of dynamic shared memory", TC_SMEM_BYTES);
         return GF_ERR_CUDA;
     }
+    // host copy of the fp32 ambient output layer (travels by value in the kernel arguments)
+    if (cudaMemcpyAsync(m->w_amb2_host, m->w + m->dev.a_w2, sizeof(float) * 256, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(img);
+        set_error("tc pack: cannot read back the ambient output layer");
+        return GF_ERR_CUDA;
+    }
     m->tc_blob = img;
     m->tc_bytes = WB_TOTAL;
     return GF_OK;
@@ -529,7 +562,7 @@ int field_tc_launch(const GfModel* model, const FieldTcIO& io, cudaStream_t st) 
     a.pos = model->dev.pos; a.amb = model->dev.amb; a.bound = model->dev.bound;
     a.wimg = (const uint8_t*)m->tc_blob;
     a.bias_ind = model->dev.ind ? model->dev.w + model->dev.c_bind : nullptr;
-    a.w_amb2 = model->dev.w + model->dev.a_w2;
+    memcpy(a.w_amb2, m->w_amb2_host, sizeof(a.w_amb2));
     a.io = io;
     a.dbg = m->tc_dbg;
     uint32_t grid = (uint32_t)model->num_sms;

@@ -63,13 +63,17 @@ __device__ __forceinline__ void corner_index2(const GridLevels& lv, int l, uint3
     }
 }
 
-// NL consecutive levels of the 3-D grid with ALL 8*NL corner loads issued before any is consumed
-// (memory-level parallelism: the gathers are L2-latency bound).  x,y,z already mapped to [0,1]
-// (grid.py:149).  Interpolation arithmetic and accumulation order are the reference's (bit-identical
-// to k_grid_forward).  out[i] = the 2 channels of level l0+i.
-template <int NL>
+// NL consecutive levels of the 3-D grid with ALL corner loads issued before any is consumed (memory-level
+// parallelism: the gathers are latency bound).  x,y,z already mapped to [0,1] (grid.py:149).
+// FAST = false: interpolation arithmetic and accumulation order are the reference's (bit-identical to k_grid_forward).
+// FAST = true (tensor-core path, features are rounded to fp16 afterwards): levels whose index drops z (sz == 0, the
+// "tiled" quirk of gridencoder.cu:72) fetch their 4 distinct corners once instead of 8 (w_z0 + w_z1 = 1).
+// Out-of-range inputs return 0 (gridencoder.cu:110-135): handled by sampling a clamped point and zeroing the result, so
+// no load is predicated.  out[i] = the 2 channels of level l0+i.
+template <int NL, bool FAST = false>
 __device__ __forceinline__ void grid3_levels(const GridDesc& g, int l0, float x, float y, float z, float2 (&out)[NL]) {
     const bool oob = x < 0 || x > 1 || y < 0 || y > 1 || z < 0 || z > 1;
+    if (oob) { x = 0.5f; y = 0.5f; z = 0.5f; }
     float fx[NL], fy[NL], fz[NL];
     float2 v[NL][8];
     #pragma unroll
@@ -81,31 +85,51 @@ __device__ __forceinline__ void grid3_levels(const GridDesc& g, int l0, float x,
         px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy); pz = __fsub_rn(pz, (float)gz);
         if (g.interp == 1) { px = smooth_(px); py = smooth_(py); pz = smooth_(pz); }
         fx[i] = px; fy[i] = py; fz[i] = pz;
-        uint32_t idx[8];
-        corner_index3(g.lv, l, gx, gy, gz, idx);
         const float2* __restrict__ tab = g.table + g.lv.offset[l];
-        #pragma unroll
-        for (int c = 0; c < 8; c++) v[i][c] = oob ? make_float2(0.f, 0.f) : __ldg(tab + idx[c]);
+        if (FAST && g.lv.sz[l] == 0 && !g.lv.hashed[l]) {
+            uint32_t idx[4];
+            const uint32_t sy = g.lv.sy[l], mask = g.lv.mask[l], b = gx + gy * sy;
+            #pragma unroll
+            for (int c = 0; c < 4; c++) idx[c] = (b + (c & 1) + (c >> 1) * sy) & mask;
+            #pragma unroll
+            for (int c = 0; c < 4; c++) v[i][c] = __ldg(tab + idx[c]);
+        } else {
+            uint32_t idx[8];
+            corner_index3(g.lv, l, gx, gy, gz, idx);
+            #pragma unroll
+            for (int c = 0; c < 8; c++) v[i][c] = __ldg(tab + idx[c]);
+        }
     }
     #pragma unroll
     for (int i = 0; i < NL; i++) {
+        const int l = l0 + i;
         const float px = fx[i], py = fy[i], pz = fz[i];
         const float qx = __fsub_rn(1.0f, px), qy = __fsub_rn(1.0f, py), qz = __fsub_rn(1.0f, pz);
         float r0 = 0.f, r1 = 0.f;
-        #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            // w = ((1 * wx) * wy) * wz in the reference's order (d = 0,1,2)
-            const float w = __fmul_rn(__fmul_rn((c & 1) ? px : qx, ((c >> 1) & 1) ? py : qy), (c >> 2) ? pz : qz);
-            r0 = __fmaf_rn(w, v[i][c].x, r0);
-            r1 = __fmaf_rn(w, v[i][c].y, r1);
+        if (FAST && g.lv.sz[l] == 0 && !g.lv.hashed[l]) {
+            #pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float w = __fmul_rn((c & 1) ? px : qx, (c >> 1) ? py : qy);
+                r0 = __fmaf_rn(w, v[i][c].x, r0);
+                r1 = __fmaf_rn(w, v[i][c].y, r1);
+            }
+        } else {
+            #pragma unroll
+            for (int c = 0; c < 8; c++) {
+                // w = ((1 * wx) * wy) * wz in the reference's order (d = 0,1,2)
+                const float w = __fmul_rn(__fmul_rn((c & 1) ? px : qx, ((c >> 1) & 1) ? py : qy), (c >> 2) ? pz : qz);
+                r0 = __fmaf_rn(w, v[i][c].x, r0);
+                r1 = __fmaf_rn(w, v[i][c].y, r1);
+            }
         }
-        out[i] = make_float2(r0, r1);
+        out[i] = oob ? make_float2(0.f, 0.f) : make_float2(r0, r1);
     }
 }
 
 template <int NL>
 __device__ __forceinline__ void grid2_levels(const GridDesc& g, int l0, float x, float y, float2 (&out)[NL]) {
     const bool oob = x < 0 || x > 1 || y < 0 || y > 1;
+    if (oob) { x = 0.5f; y = 0.5f; }
     float fx[NL], fy[NL];
     float2 v[NL][4];
     #pragma unroll
@@ -121,7 +145,7 @@ __device__ __forceinline__ void grid2_levels(const GridDesc& g, int l0, float x,
         corner_index2(g.lv, l, gx, gy, idx);
         const float2* __restrict__ tab = g.table + g.lv.offset[l];
         #pragma unroll
-        for (int c = 0; c < 4; c++) v[i][c] = oob ? make_float2(0.f, 0.f) : __ldg(tab + idx[c]);
+        for (int c = 0; c < 4; c++) v[i][c] = __ldg(tab + idx[c]);
     }
     #pragma unroll
     for (int i = 0; i < NL; i++) {
@@ -134,7 +158,7 @@ __device__ __forceinline__ void grid2_levels(const GridDesc& g, int l0, float x,
             r0 = __fmaf_rn(w, v[i][c].x, r0);
             r1 = __fmaf_rn(w, v[i][c].y, r1);
         }
-        out[i] = make_float2(r0, r1);
+        out[i] = oob ? make_float2(0.f, 0.f) : make_float2(r0, r1);
     }
 }
 

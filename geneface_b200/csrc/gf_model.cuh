@@ -119,6 +119,7 @@ struct GfModel {
     float* scratch_bias;    // device float[256] for gf_field_forward
     void* tc_blob;          // packed fp16 tensor-core weights (device), built lazily
     size_t tc_bytes;
+    float w_amb2_host[256]; // fp32 ambient output layer [2][128] (host copy, passed by value to k_field_tc)
     float* tc_dbg;          // diagnostics buffer for the tcgen05 kernel (gf_tc_debug) or null
     int num_sms;
     int profiling, ev_used;
