@@ -267,7 +267,7 @@ __device__ __forceinline__ void gather2_half(const GridDesc& g, float vx, float 
 // ------------------------------------------------------------------------------------------
 struct TcArgs {
     GridDesc pos, amb;
-    float bound;
+    float bound, inv2b;
     const uint8_t* wimg;        // WB_TOTAL bytes, global
     const float* bias_ind;      // [128] fp32 (packed fp32 blob, c_bind) or null
     float w_amb2[256];          // [2][128] fp32 ambient output layer, by value: FFMA reads it straight from the constant bank
@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_field_tc(const TcArgs a) {
         // ---- 3D grid: this thread takes levels 8*half .. 8*half+7 -> fp16 hi into F[row][k 16h..16h+15], residual into k 32+16h.. ------
         {
             // rows past the end of the list sample the centre (results are discarded)
-            const float ux = valid ? to_unit(x, a.bound) : 0.5f, uy = to_unit(y, a.bound), uz = to_unit(z, a.bound);
+            // (x + b) / (2b) as a multiply: exact for power-of-two bounds, <= 1 ulp otherwise (features are rounded to fp16 anyway)
+            const float ux = valid ? (x + a.bound) * a.inv2b : 0.5f, uy = (y + a.bound) * a.inv2b, uz = (z + a.bound) * a.inv2b;
             // `half` is warp-uniform: two copies of the code so that every per-level constant is an immediate constant-bank operand
             if (half == 0) gather3_half<0>(a.pos, ux, uy, uz, F, row);
             else gather3_half<1>(a.pos, ux, uy, uz, F, row);
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_field_tc(const TcArgs a) {
         }
         // ---- 2D ambient grid: levels 8*half .. +7 -> F[row][k 32+16h .. 32+16h+15] -------------------------------------------------------------------
         {
-            const float vx = to_unit(ax, 1.0f), vy = to_unit(ay, 1.0f);
+            const float vx = (ax + 1.0f) * 0.5f, vy = (ay + 1.0f) * 0.5f;
             if (half == 0) gather2_half<0>(a.amb, vx, vy, F, row);
             else gather2_half<1>(a.amb, vx, vy, F, row);
         }
@@ -559,7 +560,7 @@ int field_tc_launch(const GfModel* model, const FieldTcIO& io, cudaStream_t st) 
     int rc = ensure_tc_pack(m, st);
     if (rc) return rc;
     TcArgs a;
-    a.pos = model->dev.pos; a.amb = model->dev.amb; a.bound = model->dev.bound;
+    a.pos = model->dev.pos; a.amb = model->dev.amb; a.bound = model->dev.bound; a.inv2b = 0.5f / model->dev.bound;
     a.wimg = (const uint8_t*)m->tc_blob;
     a.bias_ind = model->dev.ind ? model->dev.w + model->dev.c_bind : nullptr;
     memcpy(a.w_amb2, m->w_amb2_host, sizeof(a.w_amb2));

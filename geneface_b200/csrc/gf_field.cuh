@@ -25,6 +25,7 @@ struct GridLevels {
 
 struct GridDesc {
     const float2* table;   // [sum hsize] entries of 2 floats
+    const float2* lbase[16];   // table + offset[l]: one 64-bit base per level (address = IMAD.WIDE(idx, 8, base))
     GridLevels lv;
     uint32_t gridtype;     // 0 hash, 1 tiled
     uint32_t interp;       // 0 linear, 1 smoothstep
@@ -85,7 +86,7 @@ __device__ __forceinline__ void grid3_levels(const GridDesc& g, int l0, float x,
         px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy); pz = __fsub_rn(pz, (float)gz);
         if (g.interp == 1) { px = smooth_(px); py = smooth_(py); pz = smooth_(pz); }
         fx[i] = px; fy[i] = py; fz[i] = pz;
-        const float2* __restrict__ tab = g.table + g.lv.offset[l];
+        const float2* __restrict__ tab = g.lbase[l];
         if (FAST && g.lv.sz[l] == 0 && !g.lv.hashed[l]) {
             uint32_t idx[4];
             const uint32_t sy = g.lv.sy[l], mask = g.lv.mask[l], b = gx + gy * sy;
@@ -143,7 +144,7 @@ __device__ __forceinline__ void grid2_levels(const GridDesc& g, int l0, float x,
         fx[i] = px; fy[i] = py;
         uint32_t idx[4];
         corner_index2(g.lv, l, gx, gy, idx);
-        const float2* __restrict__ tab = g.table + g.lv.offset[l];
+        const float2* __restrict__ tab = g.lbase[l];
         #pragma unroll
         for (int c = 0; c < 4; c++) v[i][c] = __ldg(tab + idx[c]);
     }

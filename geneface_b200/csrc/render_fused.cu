@@ -768,6 +768,11 @@ GF_API int gf_model_create(const GfModelDesc* d, GfModel** out, gf_stream_t stre
     md.pos.table = reinterpret_cast<const float2*>(d->pos_embeddings); md.pos.lv = lv_host[0]; md.pos.gridtype = d->gridtype; md.pos.interp = d->interp;
     md.amb.table = reinterpret_cast<const float2*>(d->amb_embeddings); md.amb.lv = lv_host[1]; md.amb.gridtype = d->gridtype; md.amb.interp = d->interp;
     md.torso.table = reinterpret_cast<const float2*>(d->torso_embeddings); md.torso.lv = lv_host[2]; md.torso.gridtype = 1; md.torso.interp = 0;   // radnerf_torso.py:36 ('tiledgrid', linear)
+    for (int l = 0; l < 16; l++) {
+        md.pos.lbase[l] = md.pos.table + lv_host[0].offset[l];
+        md.amb.lbase[l] = md.amb.table + lv_host[1].offset[l];
+        md.torso.lbase[l] = md.torso.table ? md.torso.table + lv_host[2].offset[l] : nullptr;
+    }
     // tensor-core pack (field_tc.cu) is built lazily on first precision-1 use
     cudaFuncSetAttribute(k_field_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, FP32_SMEM_FLOATS * (int)sizeof(float));
     cudaFuncSetAttribute(k_torso_field, cudaFuncAttributeMaxDynamicSharedMemorySize, TORSO_SMEM_FLOATS * (int)sizeof(float));
