@@ -302,7 +302,9 @@ def main():
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(conds_h[0].numel() * 4 + 16 * 4 + 6 * 4),
                 "d2h_bytes_per_step": int(host_rgb8.numel())},
         "gpu_launches": launches * args.steps,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": 236503296 if args.precision == "fp16" else None,   # dram read+write bytes per launch (= one 8.4 M-sample round), profiles/r01_summary.md
+                     "algorithmic_bytes_per_launch": samples_per_frame // 4 * HEAD_SAMPLE_BYTES,
                      "kernel": "k_field_tc" if args.precision == "fp16" else "k_field_fp32", "kernel_ms_per_frame": field_ms_per_frame,
                      "kernel_share_of_step": field_ms_per_frame / (ms_res / args.steps), "peak_source": peaks["source"],
                      "tensor_tflops": tflops, "tensor_frac_of_bf16_peak": tflops / peaks["bf16_tflops"],
