@@ -15,7 +15,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 _SO = os.path.join(_PKG, "libgfrender.so")
 _INCLUDE = os.path.join(os.path.dirname(_PKG), "include")
 
-SOURCES = ["api.cu", "raymarch_ops.cu", "encoders.cu", "render_fused.cu", "field_tc.cu"]
+SOURCES = ["api.cu", "raymarch_ops.cu", "encoders.cu", "render_fused.cu", "field_tc.cu", "field_tc_split.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",

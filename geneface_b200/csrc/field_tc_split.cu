@@ -1,0 +1,513 @@
+// libgfrender: warp-specialised, two-kernel tcgen05 field pipeline (precision = 1, default mode).
+//
+// The single fused kernel (field_tc.cu) serialises, per tile, {3-D gather -> 2 MMA layers -> 2-D gather -> 5 MMA layers}:
+// the gathers (L1/L2 latency) and the MMA chain (tensor latency) cannot overlap because only two tiles fit in tensor
+// memory (a 128-row tile needs 128 accumulator + 64..128 operand columns of the 512) and the 184 KB of weights leave no
+// shared memory for look-ahead feature tiles.  Splitting the field at the ambient coordinate halves the weights each
+// kernel keeps resident, which buys a 6-deep ring of feature tiles and lets DEDICATED PRODUCER WARPS gather ahead while
+// two consumer streams run the MMA chain back to back:
+//
+//   k_tc_amb     producers (8 warps): 3-D grid gather -> fp16 hi/lo feature tile in the smem ring (+ hi copy to HBM)
+//                consumers (2 x 4 warps, one thread per sample row = TMEM lane):
+//                    ambient L0 (split precision, SS) -> ambient L1 (split precision, TS) -> 128->2 in fp32 -> tanh
+//                    -> ambient coordinate (8 B/sample) to HBM
+//   k_tc_sigcol  producers: 64 B/sample of position features back from HBM + 2-D ambient-grid gather -> smem ring
+//                consumers: sigma L0 (SS) -> sigma L1 (TS) -> merged sigma-L2 x colour-L0 (+ SH, SS) -> colour L1 -> sigma, rgb
+//
+// Producer -> consumer hand-off: one `full` mbarrier per ring slot (256 producer arrivals, generic->async proxy fence before
+// the arrive), one `empty` mbarrier per slot (arrived by the stream leader once the tcgen05.commit of the last MMA reading
+// the slot has completed).  Extra HBM traffic: 64 + 8 B/sample written and read once (4.8 GB/frame at 512x512x128, <10 %
+// of the algorithmic gather bytes); everything else about the arithmetic is identical to field_tc.cu.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "gf_model.cuh"
+#include "gf_tc.cuh"
+
+namespace gf {
+
+constexpr int SP_THREADS = 512;        // warps 0-7 producers, 8-11 consumer stream 0, 12-15 consumer stream 1
+constexpr int SP_NSLOT = 6;            // feature-tile ring depth
+constexpr uint32_t SP_TILE_BYTES = 128 * 128;
+
+// ---- weight images ---------------------------------------------------------------------------------------------------
+// kernel A (80 KB)
+constexpr uint32_t WA_A0 = 0;                               // [128]: k 0..31 Wa0_hi, k 32..63 Wa0_lo
+constexpr uint32_t WA_A1H = WA_A0 + 128 * 128;              // 2 chunks x [128]
+constexpr uint32_t WA_A1L = WA_A1H + 2 * 128 * 128;
+constexpr uint32_t WA_TOTAL = WA_A1L + 2 * 128 * 128;       // 81,920
+// kernel B (104 KB)
+constexpr uint32_t WB2_SIG0 = 0;                            // [128] k 0..63
+constexpr uint32_t WB2_SIG1 = WB2_SIG0 + 128 * 128;         // 2 chunks x [128]
+constexpr uint32_t WB2_MRG = WB2_SIG1 + 2 * 128 * 128;      // 2 chunks x [144]
+constexpr uint32_t WB2_COL1 = WB2_MRG + 2 * 144 * 128;      // 2 chunks x [16]
+constexpr uint32_t WB2_SH = WB2_COL1 + 2 * 16 * 128;        // [128]: k 0..15 colour-L0 SH columns
+constexpr uint32_t WB2_TOTAL = WB2_SH + 128 * 128;          // 106,496
+static_assert(WA_TOTAL == 81920 && WB2_TOTAL == 106496, "image sizes");
+static_assert(WB2_MRG % 1024 == 0 && WB2_COL1 % 1024 == 0 && WB2_SH % 1024 == 0, "1024-byte aligned blocks");
+
+// shared-memory layout (same skeleton for both kernels; W = weight image bytes)
+template <uint32_t W>
+struct SpSmem {
+    static constexpr uint32_t F = W;
+    static constexpr uint32_t BIAS = F + SP_NSLOT * SP_TILE_BYTES;   // 128 floats
+    static constexpr uint32_t BAR = BIAS + 512;                      // wbar, full[NSLOT], empty[NSLOT], mma[2]
+    static constexpr uint32_t TMEM = BAR + 8 * (1 + 2 * SP_NSLOT + 2);
+    static constexpr uint32_t TOTAL = TMEM + 16;
+    static constexpr uint32_t BYTES = TOTAL + 1024;
+};
+static_assert(SpSmem<WB2_TOTAL>::BYTES <= 232448, "exceeds 227 KB");
+
+// TMEM columns per consumer stream (256): D at +0; ambient phase A_hi +128 / A_lo +192; later layers A at +144
+constexpr uint32_t SP_TM_STREAM = 256, SP_TM_AHI = 128, SP_TM_ALO = 192, SP_TM_A = 144;
+
+struct TcPackSrc2 {
+    const float *a0, *a1, *s0, *s1, *s2, *c0, *c1;
+    int cond, ind, G;
+};
+
+__device__ __forceinline__ void put_half2(uint8_t* img, uint32_t block, uint32_t rows, uint32_t n, uint32_t k, float v, bool lo) {
+    const uint32_t chunk = k >> 6, kk = k & 63;
+    const uint32_t off = block + chunk * rows * 128 + sw128(n, kk >> 3) + (kk & 7) * 2;
+    const __half hi = __float2half_rn(v);
+    *reinterpret_cast<__half*>(img + off) = lo ? __float2half_rn(v - __half2float(hi)) : hi;
+}
+
+__global__ void k_tc_pack_split(TcPackSrc2 s, uint8_t* __restrict__ imgA, uint8_t* __restrict__ imgB) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (n, k) of a 144 x 128 index space
+    const int n = i / 128, k = i % 128;
+    if (n >= 144) return;
+    const int a_in = 32 + s.cond, c_in = 16 + s.G + s.ind;
+    if (n < 128) {
+        if (k < 32) {
+            const float w = s.a0[(size_t)n * a_in + k];
+            put_half2(imgA, WA_A0, 128, n, k, w, false);
+            put_half2(imgA, WA_A0, 128, n, 32 + k, w, true);
+        }
+        const float w1 = s.a1[(size_t)n * 128 + k];
+        put_half2(imgA, WA_A1H, 128, n, k, w1, false);
+        put_half2(imgA, WA_A1L, 128, n, k, w1, true);
+        if (k < 64) put_half2(imgB, WB2_SIG0, 128, n, k, s.s0[(size_t)n * 64 + k], false);
+        put_half2(imgB, WB2_SIG1, 128, n, k, s.s1[(size_t)n * 128 + k], false);
+        float acc = 0.f;
+        for (int j = 0; j < s.G; j++) acc = fmaf(s.c0[(size_t)n * c_in + 16 + j], s.s2[(size_t)(1 + j) * 128 + k], acc);
+        put_half2(imgB, WB2_MRG, 144, n, k, acc, false);
+        if (k < 16) put_half2(imgB, WB2_SH, 128, n, k, s.c0[(size_t)n * c_in + k], false);
+    } else {
+        put_half2(imgB, WB2_MRG, 144, n, k, n == 128 ? s.s2[k] : 0.f, false);
+    }
+    if (n < 16) put_half2(imgB, WB2_COL1, 16, n, k, n < 3 ? s.c1[(size_t)n * 128 + k] : 0.f, false);
+}
+
+struct SpArgs {
+    GridDesc grid;              // A: 3-D position grid; B: 2-D ambient grid
+    float bound, inv2b;
+    const uint8_t* wimg;
+    const float* bias;          // A: per-frame cond bias [128]; B: individual-code bias [128] or null
+    float w_amb2[256];          // A only
+    FieldTcIO io;
+    float* dbg;
+};
+
+// common prologue: barriers, TMEM, weights, bias.  Returns the TMEM base.
+template <uint32_t W>
+__device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, const SpArgs& a, const uint32_t* cuts, int ncuts) {
+    using L = SpSmem<W>;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    float* bias = reinterpret_cast<float*>(smem + L::BIAS);
+    if (tid == 0) {
+        mbar_init(sbase + L::BAR, 1);
+        for (int s = 0; s < SP_NSLOT; s++) {
+            mbar_init(sbase + L::BAR + 8 * (1 + s), 256);               // full: every producer thread arrives
+            mbar_init(sbase + L::BAR + 8 * (1 + SP_NSLOT + s), 1);      // empty: the stream leader arrives
+        }
+        mbar_init(sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT), 1);
+        mbar_init(sbase + L::BAR + 8 * (2 + 2 * SP_NSLOT), 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(sbase + L::TMEM, 512);
+    if (tid < 128) bias[tid] = a.bias ? a.bias[tid] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        mbar_expect_tx(sbase + L::BAR, W);
+        for (int i = 0; i < ncuts; i++) bulk_g2s(sbase + cuts[i], a.wimg + cuts[i], cuts[i + 1] - cuts[i], sbase + L::BAR);
+    }
+    mbar_wait(sbase + L::BAR, 0);
+    return *reinterpret_cast<uint32_t*>(smem + L::TMEM);
+}
+
+// ======================================================================================================================
+// kernel A: 3-D gather -> ambient branch -> ambient coordinate + fp16 position features
+// ======================================================================================================================
+template <int HALF>
+__device__ __forceinline__ void produce_pos(const GridDesc& g, float ux, float uy, float uz, uint8_t* F, uint32_t row, uint4* hi_out) {
+    #pragma unroll
+    for (int b = 0; b < 2; b++) {
+        float2 f[4];
+        grid3_levels<4, true>(g, 8 * HALF + 4 * b, ux, uy, uz, f);
+        const uint4 hi = make_uint4(pack_h2(f[0].x, f[0].y), pack_h2(f[1].x, f[1].y), pack_h2(f[2].x, f[2].y), pack_h2(f[3].x, f[3].y));
+        *reinterpret_cast<uint4*>(F + sw128(row, 2 * HALF + b)) = hi;
+        *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * HALF + b)) =
+            make_uint4(pack_h2(h_resid(f[0].x), h_resid(f[0].y)), pack_h2(h_resid(f[1].x), h_resid(f[1].y)),
+                       pack_h2(h_resid(f[2].x), h_resid(f[2].y)), pack_h2(h_resid(f[3].x), h_resid(f[3].y)));
+        if (hi_out) hi_out[b] = hi;
+    }
+}
+
+__global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
+    using L = SpSmem<WA_TOTAL>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t M = a.io.M_dev ? *a.io.M_dev : a.io.M_host;
+    const uint32_t cuts[4] = {0, WA_A1H, WA_A1L, WA_TOTAL};
+    const uint32_t tmem_base = sp_setup<WA_TOTAL>(smem, sbase, a, cuts, 3);
+    const float* bias_cond = reinterpret_cast<const float*>(smem + L::BIAS);
+    const uint32_t bar_full = sbase + L::BAR + 8, bar_empty = sbase + L::BAR + 8 * (1 + SP_NSLOT);
+    const uint32_t num_tiles = (M + 127) / 128;
+    const uint32_t my_tiles = num_tiles > blockIdx.x ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp < 8) {
+        // ------------------------------------------------ producers ------------------------------------------------
+        const uint32_t half = tid >> 7, row = tid & 127;
+        for (uint32_t j = 0; j < my_tiles; j++) {
+            const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
+            const uint32_t i = tile * 128 + row;
+            const bool valid = i < M;
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (valid) {
+                if (a.io.pos4) { const float4 p = a.io.pos4[i]; x = p.x; y = p.y; z = p.z; }
+                else { x = a.io.xyzs[3 * (size_t)i]; y = a.io.xyzs[3 * (size_t)i + 1]; z = a.io.xyzs[3 * (size_t)i + 2]; }
+            }
+            const float ux = valid ? (x + a.bound) * a.inv2b : 0.5f, uy = (y + a.bound) * a.inv2b, uz = (z + a.bound) * a.inv2b;
+            mbar_wait(bar_empty + 8 * slot, (n & 1) ^ 1);                 // slot released by the consumer of its previous use
+            uint8_t* F = smem + L::F + slot * SP_TILE_BYTES;
+            uint4 hi[2];
+            if (half == 0) produce_pos<0>(a.grid, ux, uy, uz, F, row, hi);
+            else produce_pos<1>(a.grid, ux, uy, uz, F, row, hi);
+            if (valid) {
+                a.io.feat_hi[(size_t)i * 4 + 2 * half] = hi[0];
+                a.io.feat_hi[(size_t)i * 4 + 2 * half + 1] = hi[1];
+            }
+            fence_async_smem();
+            mbar_arrive(bar_full + 8 * slot);
+        }
+    } else {
+        // ------------------------------------------------ consumers ------------------------------------------------
+        const uint32_t stream = (warp - 8) >> 2, row = tid & 127;
+        const uint32_t t_d = tmem_base + (((warp & 3) * 32) << 16) + stream * SP_TM_STREAM;
+        const uint32_t m_d = tmem_base + stream * SP_TM_STREAM;
+        const uint32_t bar_mma = sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT + stream);
+        const uint32_t w_addr = sbase;
+        const bool leader = row == 0;
+        uint32_t phase = 0;
+        for (uint32_t j = stream; j < my_tiles; j += 2) {
+            const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
+            const uint32_t i = tile * 128 + row;
+            float* dbg = (a.dbg && tile == 0) ? a.dbg + (size_t)row * 144 : nullptr;
+            const uint32_t f_addr = sbase + L::F + slot * SP_TILE_BYTES;
+            tc_fence_before();
+            bar_named(1 + stream, 128);                                   // previous tile's accumulator reads are done
+            if (leader) {
+                mbar_wait(bar_full + 8 * slot, n & 1);
+                tc_fence_after();
+                // split precision: F_hi W_hi + F_lo W_hi + F_hi W_lo  (K = 32 each)
+                #pragma unroll
+                for (int k = 0; k < 2; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WA_A0 + 32 * k), idesc_f16(128), k);
+                #pragma unroll
+                for (int k = 0; k < 2; k++) mma_ss(m_d, smem_desc(f_addr + 64 + 32 * k), smem_desc(w_addr + WA_A0 + 32 * k), idesc_f16(128), 1);
+                #pragma unroll
+                for (int k = 0; k < 2; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WA_A0 + 64 + 32 * k), idesc_f16(128), 1);
+                mma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, phase); phase ^= 1;
+            tc_fence_after();
+            if (leader) mbar_arrive(bar_empty + 8 * slot);                // the feature tile has been consumed
+            epilogue_relu_to_A_n<true, 4>(t_d, t_d + SP_TM_AHI, t_d + SP_TM_ALO, 0, bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);
+            tc_fence_before();
+            bar_named(1 + stream, 128);
+            if (leader) {
+                tc_fence_after();
+                #pragma unroll
+                for (int k = 0; k < 8; k++)
+                    mma_ts(m_d, m_d + SP_TM_AHI + 8 * k, smem_desc(w_addr + WA_A1H + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), k);
+                #pragma unroll
+                for (int k = 0; k < 8; k++)
+                    mma_ts(m_d, m_d + SP_TM_ALO + 8 * k, smem_desc(w_addr + WA_A1H + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), 1);
+                #pragma unroll
+                for (int k = 0; k < 8; k++)
+                    mma_ts(m_d, m_d + SP_TM_AHI + 8 * k, smem_desc(w_addr + WA_A1L + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), 1);
+                mma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, phase); phase ^= 1;
+            tc_fence_after();
+            // ambient output layer (128 -> 2) in fp32 from the accumulator, weights from the constant bank; tanh
+            float s0 = 0.f, s1 = 0.f;
+            #pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float v[32];
+                tmem_ld32(t_d + 32 * c, v);
+                if (dbg) {
+                    #pragma unroll
+                    for (int q = 0; q < 32; q++) dbg[1 * 128 * 144 + 32 * c + q] = v[q];
+                }
+                #pragma unroll
+                for (int q = 0; q < 32; q++) {
+                    const float r = fmaxf(v[q], 0.f);
+                    s0 = fmaf(r, a.w_amb2[32 * c + q], s0);
+                    s1 = fmaf(r, a.w_amb2[128 + 32 * c + q], s1);
+                }
+            }
+            if (dbg) { dbg[2 * 128 * 144 + 0] = s0; dbg[2 * 128 * 144 + 1] = s1; }
+            if (i < M) a.io.amb_pos[i] = make_float2(tanhf(s0), tanhf(s1));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ======================================================================================================================
+// kernel B: features + 2-D gather -> sigma / colour
+// ======================================================================================================================
+template <int HALF>
+__device__ __forceinline__ void produce_amb(const GridDesc& g, float vx, float vy, uint8_t* F, uint32_t row) {
+    float2 f[8];
+    grid2_levels<8>(g, 8 * HALF, vx, vy, f);
+    #pragma unroll
+    for (int u = 0; u < 2; u++)
+        *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * HALF + u)) =
+            make_uint4(pack_h2(f[4 * u].x, f[4 * u].y), pack_h2(f[4 * u + 1].x, f[4 * u + 1].y),
+                       pack_h2(f[4 * u + 2].x, f[4 * u + 2].y), pack_h2(f[4 * u + 3].x, f[4 * u + 3].y));
+}
+
+__global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
+    using L = SpSmem<WB2_TOTAL>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t M = a.io.M_dev ? *a.io.M_dev : a.io.M_host;
+    const uint32_t cuts[5] = {0, WB2_SIG1, WB2_MRG, WB2_COL1, WB2_TOTAL};
+    const uint32_t tmem_base = sp_setup<WB2_TOTAL>(smem, sbase, a, cuts, 4);
+    const float* bias_ind = reinterpret_cast<const float*>(smem + L::BIAS);
+    const uint32_t bar_full = sbase + L::BAR + 8, bar_empty = sbase + L::BAR + 8 * (1 + SP_NSLOT);
+    const uint32_t num_tiles = (M + 127) / 128;
+    const uint32_t my_tiles = num_tiles > blockIdx.x ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp < 8) {
+        // ------------------------------------------------ producers ------------------------------------------------
+        const uint32_t half = tid >> 7, row = tid & 127;
+        for (uint32_t j = 0; j < my_tiles; j++) {
+            const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
+            const uint32_t i = tile * 128 + row;
+            const bool valid = i < M;
+            uint4 hi0 = make_uint4(0, 0, 0, 0), hi1 = hi0;
+            float2 ap = make_float2(0.f, 0.f);
+            if (valid) {
+                hi0 = a.io.feat_hi[(size_t)i * 4 + 2 * half];
+                hi1 = a.io.feat_hi[(size_t)i * 4 + 2 * half + 1];
+                ap = a.io.amb_pos[i];
+            }
+            const float vx = (ap.x + 1.0f) * 0.5f, vy = (ap.y + 1.0f) * 0.5f;
+            mbar_wait(bar_empty + 8 * slot, (n & 1) ^ 1);
+            uint8_t* F = smem + L::F + slot * SP_TILE_BYTES;
+            *reinterpret_cast<uint4*>(F + sw128(row, 2 * half)) = hi0;
+            *reinterpret_cast<uint4*>(F + sw128(row, 2 * half + 1)) = hi1;
+            if (half == 0) produce_amb<0>(a.grid, vx, vy, F, row);
+            else produce_amb<1>(a.grid, vx, vy, F, row);
+            fence_async_smem();
+            mbar_arrive(bar_full + 8 * slot);
+        }
+    } else {
+        // ------------------------------------------------ consumers ------------------------------------------------
+        const uint32_t stream = (warp - 8) >> 2, row = tid & 127;
+        const uint32_t t_d = tmem_base + (((warp & 3) * 32) << 16) + stream * SP_TM_STREAM;
+        const uint32_t m_d = tmem_base + stream * SP_TM_STREAM;
+        const uint32_t t_a = t_d + SP_TM_A, m_a = m_d + SP_TM_A;
+        const uint32_t bar_mma = sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT + stream);
+        const uint32_t w_addr = sbase;
+        const bool leader = row == 0;
+        uint32_t phase = 0;
+        for (uint32_t j = stream; j < my_tiles; j += 2) {
+            const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
+            const uint32_t i = tile * 128 + row;
+            const bool valid = i < M;
+            float* dbg = (a.dbg && tile == 0) ? a.dbg + (size_t)row * 144 : nullptr;
+            uint8_t* F = smem + L::F + slot * SP_TILE_BYTES;
+            const uint32_t f_addr = sbase + L::F + slot * SP_TILE_BYTES;
+            // view direction of this row's ray (for the SH K-extension of the colour layer)
+            float dx = 0.f, dy = 0.f, dz = 1.f;
+            if (valid) {
+                if (a.io.pos4) {
+                    const int ray = __float_as_int(a.io.pos4[i].w);
+                    dx = __ldg(a.io.rays_d + 3 * (size_t)ray); dy = __ldg(a.io.rays_d + 3 * (size_t)ray + 1); dz = __ldg(a.io.rays_d + 3 * (size_t)ray + 2);
+                } else { dx = a.io.dirs[3 * (size_t)i]; dy = a.io.dirs[3 * (size_t)i + 1]; dz = a.io.dirs[3 * (size_t)i + 2]; }
+            }
+            tc_fence_before();
+            bar_named(1 + stream, 128);
+            // ---- sigma layer 0: D = F[:, 0:64] @ Ws0^T ------------------------------------------------------------
+            if (leader) {
+                mbar_wait(bar_full + 8 * slot, n & 1);
+                tc_fence_after();
+                #pragma unroll
+                for (int k = 0; k < 4; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WB2_SIG0 + 32 * k), idesc_f16(128), k);
+                mma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, phase); phase ^= 1;
+            tc_fence_after();
+            epilogue_relu_to_A_n<false, 4>(t_d, t_a, 0, 0, nullptr, dbg ? dbg + 3 * 128 * 144 : nullptr);
+            tc_fence_before();
+            bar_named(1 + stream, 128);
+            // ---- sigma layer 1 -----------------------------------------------------------------------------------------
+            if (leader) {
+                tc_fence_after();
+                #pragma unroll
+                for (int k = 0; k < 8; k++)
+                    mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_SIG1 + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), k);
+                mma_commit(bar_mma);
+            }
+            // SH(dir) -> F[row][k 32..47]: the sigma-layer-0 MMA that read this slot has completed (waited above)
+            {
+                float sh[16];
+                sh4(dx, dy, dz, sh);
+                uint32_t p[8];
+                #pragma unroll
+                for (int q = 0; q < 8; q++) p[q] = pack_h2(sh[2 * q], sh[2 * q + 1]);
+                *reinterpret_cast<uint4*>(F + sw128(row, 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+                *reinterpret_cast<uint4*>(F + sw128(row, 5)) = make_uint4(p[4], p[5], p[6], p[7]);
+                fence_async_smem();
+            }
+            mbar_wait(bar_mma, phase); phase ^= 1;
+            tc_fence_after();
+            epilogue_relu_to_A_n<false, 4>(t_d, t_a, 0, 0, nullptr, dbg ? dbg + 4 * 128 * 144 : nullptr);
+            tc_fence_before();
+            bar_named(1 + stream, 128);
+            // ---- merged sigma layer 2 x colour layer 0 (N = 144) + SH part (SS, K = 16, N = 128) --------------------------
+            if (leader) {
+                tc_fence_after();
+                #pragma unroll
+                for (int k = 0; k < 8; k++)
+                    mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_MRG + (k >> 2) * (144 * 128) + 32 * (k & 3)), idesc_f16(144), k);
+                mma_ss(m_d, smem_desc(f_addr + 64), smem_desc(w_addr + WB2_SH), idesc_f16(128), 1);
+                mma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, phase); phase ^= 1;
+            tc_fence_after();
+            if (leader) mbar_arrive(bar_empty + 8 * slot);                // last reader of the feature tile is done
+            float sg[4];
+            tmem_ld4(t_d + 128, sg);
+            if (dbg) dbg[5 * 128 * 144 + 128] = sg[0];
+            epilogue_relu_to_A_n<false, 4>(t_d, t_a, 0, 0, a.bias ? bias_ind : nullptr, dbg ? dbg + 5 * 128 * 144 : nullptr);
+            tc_fence_before();
+            bar_named(1 + stream, 128);
+            // ---- colour layer 1 (N = 16; 3 real outputs) -> sigmoid ---------------------------------------------------------
+            if (leader) {
+                tc_fence_after();
+                #pragma unroll
+                for (int k = 0; k < 8; k++)
+                    mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_COL1 + (k >> 2) * (16 * 128) + 32 * (k & 3)), idesc_f16(16), k);
+                mma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, phase); phase ^= 1;
+            tc_fence_after();
+            float c[4];
+            tmem_ld4(t_d, c);
+            if (dbg) { dbg[6 * 128 * 144 + 0] = c[0]; dbg[6 * 128 * 144 + 1] = c[1]; dbg[6 * 128 * 144 + 2] = c[2]; }
+            if (valid) {
+                const float sigma = __expf(sg[0]);
+                const float cr = __fdividef(1.0f, 1.0f + __expf(-c[0]));
+                const float cg = __fdividef(1.0f, 1.0f + __expf(-c[1]));
+                const float cb = __fdividef(1.0f, 1.0f + __expf(-c[2]));
+                if (a.io.out4) a.io.out4[i] = make_float4(sigma, cr, cg, cb);
+                if (a.io.sigmas) a.io.sigmas[i] = sigma;
+                if (a.io.rgbs) { a.io.rgbs[3 * (size_t)i] = cr; a.io.rgbs[3 * (size_t)i + 1] = cg; a.io.rgbs[3 * (size_t)i + 2] = cb; }
+                if (a.io.ambient) { const float2 ap = a.io.amb_pos[i]; a.io.ambient[2 * (size_t)i] = ap.x; a.io.ambient[2 * (size_t)i + 1] = ap.y; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (a.io.stat_samples && blockIdx.x == 0 && tid == 0) atomicAdd(a.io.stat_samples, (unsigned long long)M);
+}
+
+// ======================================================================================================================
+// host
+// ======================================================================================================================
+static int ensure_split_pack(GfModel* m, cudaStream_t st) {
+    if (m->tc2_blob) return GF_OK;
+    const GfModelDesc& d = m->desc;
+    if (d.hidden_dim != 128 || d.geo_feat_dim != 128) {
+        set_error("precision=1 (tcgen05) supports hidden_dim == 128 and geo_feat_dim == 128 only; use precision=0");
+        return GF_ERR_UNSUPPORTED;
+    }
+    uint8_t* img = nullptr;
+    if (cudaMalloc(&img, WA_TOTAL + WB2_TOTAL) != cudaSuccess) { cudaGetLastError(); set_error("tc pack: cudaMalloc failed"); return GF_ERR_CUDA; }
+    cudaMemsetAsync(img, 0, WA_TOTAL + WB2_TOTAL, st);
+    TcPackSrc2 s;
+    s.a0 = d.ambient_w0; s.a1 = d.ambient_w1; s.s0 = d.sigma_w0; s.s1 = d.sigma_w1; s.s2 = d.sigma_w2; s.c0 = d.color_w0; s.c1 = d.color_w1;
+    s.cond = (int)d.cond_dim; s.ind = (int)d.ind_dim; s.G = (int)d.geo_feat_dim;
+    k_tc_pack_split<<<(144 * 128 + 255) / 256, 256, 0, st>>>(s, img, img + WA_TOTAL);
+    int rc = check_launch("tc split pack");
+    if (rc) { cudaFree(img); return rc; }
+    if (cudaFuncSetAttribute(k_tc_amb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_sigcol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
+        cudaMemcpyAsync(m->w_amb2_host, m->w + m->dev.a_w2, sizeof(float) * 256, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(img);
+        set_error("tc split pack: setup failed");
+        return GF_ERR_CUDA;
+    }
+    m->tc2_blob = img;
+    return GF_OK;
+}
+
+int field_tc_split_launch(const GfModel* model, const FieldTcIO& io_in, cudaStream_t st) {
+    GfModel* m = const_cast<GfModel*>(model);
+    int rc = ensure_split_pack(m, st);
+    if (rc) return rc;
+    FieldTcIO io = io_in;
+    if (!io.feat_hi || !io.amb_pos) {
+        // stand-alone field evaluation (gf_field_forward): model-owned, grow-only scratch
+        if (io.M_dev) { set_error("field_tc_split: device-side sample count needs caller scratch"); return GF_ERR_INVALID; }
+        const size_t need = (size_t)io.M_host * (64 + 8) + 256;
+        if (m->tc_scratch_bytes < need) {
+            if (m->tc_scratch) { cudaStreamSynchronize(st); cudaFree(m->tc_scratch); m->tc_scratch = nullptr; m->tc_scratch_bytes = 0; }
+            if (cudaMalloc(&m->tc_scratch, need) != cudaSuccess) { cudaGetLastError(); set_error("field_tc_split: scratch cudaMalloc failed"); return GF_ERR_CUDA; }
+            m->tc_scratch_bytes = need;
+        }
+        io.feat_hi = reinterpret_cast<uint4*>(m->tc_scratch);
+        io.amb_pos = reinterpret_cast<float2*>((char*)m->tc_scratch + (((size_t)io.M_host * 64 + 255) & ~size_t(255)));
+    }
+    uint32_t grid = (uint32_t)model->num_sms;
+    if (!io.M_dev) {
+        const uint32_t tiles = (io.M_host + 127) / 128;
+        if (tiles < grid) grid = tiles ? tiles : 1;
+    }
+    SpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.bound = model->dev.bound; a.inv2b = 0.5f / model->dev.bound;
+    a.io = io;
+    a.dbg = m->tc_dbg;
+    a.grid = model->dev.pos;
+    a.wimg = (const uint8_t*)m->tc2_blob;
+    a.bias = io.bias_amb;
+    memcpy(a.w_amb2, m->w_amb2_host, sizeof(a.w_amb2));
+    k_tc_amb<<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
+    rc = check_launch("field_tc_split(amb)");
+    if (rc) return rc;
+    a.grid = model->dev.amb;
+    a.wimg = (const uint8_t*)m->tc2_blob + WA_TOTAL;
+    a.bias = model->dev.ind ? model->dev.w + model->dev.c_bind : nullptr;
+    k_tc_sigcol<<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
+    return check_launch("field_tc_split(sigcol)");
+}
+
+}  // namespace gf

@@ -104,6 +104,9 @@ struct FieldTcIO {
     float* ambient;
     const float* bias_amb;
     unsigned long long* stat_samples;
+    // scratch of the split (two-kernel) pipeline; null -> model-owned scratch
+    uint4* feat_hi;        // [M][4] uint4 = 32 fp16 position features per sample
+    float2* amb_pos;       // [M] ambient coordinates
 };
 
 }  // namespace gf
@@ -120,6 +123,9 @@ struct GfModel {
     void* tc_blob;          // packed fp16 tensor-core weights (device), built lazily
     size_t tc_bytes;
     float w_amb2_host[256]; // fp32 ambient output layer [2][128] (host copy, passed by value to k_field_tc)
+    void* tc2_blob;         // weight images of the split pipeline (device)
+    void* tc_scratch;       // grow-only scratch for gf_field_forward in split mode
+    size_t tc_scratch_bytes;
     float* tc_dbg;          // diagnostics buffer for the tcgen05 kernel (gf_tc_debug) or null
     int num_sms;
     int profiling, ev_used;

@@ -607,6 +607,8 @@ struct Workspace {
     float *bias_amb, *bias_deform, *bias_canon;
     uint32_t* torso_list;
     float *torso_alpha, *torso_color;
+    uint4* feat_hi;      // split tensor-core pipeline: fp16 position features, 64 B per sample
+    float2* amb_pos;     // split tensor-core pipeline: ambient coordinate per sample
     size_t bytes;
 };
 
@@ -643,6 +645,8 @@ static Workspace carve(void* base, uint32_t N) {
     w.torso_list = (uint32_t*)take(sizeof(uint32_t) * N);
     w.torso_alpha = (float*)take(sizeof(float) * N);
     w.torso_color = (float*)take(sizeof(float) * 3 * N);
+    w.feat_hi = (uint4*)take(64 * cap);
+    w.amb_pos = (float2*)take(sizeof(float2) * cap);
     w.bytes = off;
     return w;
 }
@@ -788,6 +792,8 @@ GF_API void gf_model_destroy(GfModel* m) {
     if (!m) return;
     if (m->w) cudaFree(m->w);
     if (m->tc_blob) cudaFree(m->tc_blob);
+    if (m->tc2_blob) cudaFree(m->tc2_blob);
+    if (m->tc_scratch) cudaFree(m->tc_scratch);
     if (m->scratch_bias) cudaFree(m->scratch_bias);
     for (int i = 0; i < GF_MAX_PROFILE_EVENTS; i++)
         if (m->ev[i]) cudaEventDestroy(m->ev[i]);
@@ -922,6 +928,7 @@ GF_API int gf_render_frame(const GfModel* model, const GfFrame* f, const GfOut* 
         memset(&io, 0, sizeof(io));
         io.pos4 = w.sb.pos4; io.rays_d = w.st.rays_d; io.M_dev = w.ctl + CTL_TOTAL; io.out4 = w.sb.out4; io.bias_amb = w.bias_amb;
         io.stat_samples = w.stat;
+        io.feat_hi = w.feat_hi; io.amb_pos = w.amb_pos;
         return field_tc_launch(model, io, st);
     };
     // optional CUDA-event bracket around every field launch (gf_profile_*): the dominant-kernel timing bench.py reports
