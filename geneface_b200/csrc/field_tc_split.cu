@@ -143,18 +143,95 @@ __device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, cons
 // ======================================================================================================================
 // kernel A: 3-D gather -> ambient branch -> ambient coordinate + fp16 position features
 // ======================================================================================================================
-template <int HALF>
-__device__ __forceinline__ void produce_pos(const GridDesc& g, float ux, float uy, float uz, uint8_t* F, uint32_t row, uint4* hi_out) {
+// ---- gathers with a RUN-TIME level index ------------------------------------------------------------------------------
+// The producers' code must stay small: four instruction streams (2 producer + 2 consumer warps) share each scheduler's
+// ~6 KB L0 / the SM's 32 KB L1.5 instruction cache, and the fully unrolled per-level code of field_tc.cu (72 KB of SASS)
+// left the producer warps starved for instructions (ncu: 45 % of their stall samples were no_instruction).  Here ONE
+// copy of a 4-level batch serves both halves and both batches; level constants are indexed loads from the constant bank.
+//
+// 3-D position grid, 4 consecutive levels from l0.  Levels whose index drops z (gridencoder.cu:72 quirk) or are dense fetch the
+// z+1 plane only when it exists.  Interpolation is bilinear per z-plane, then a lerp in z (the fp32 result differs from the
+// reference's corner-order sum by rounding only; it is rounded to fp16 right after).
+__device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x, float y, float z, float2 (&out)[4]) {
+    float fx[4], fy[4], fz[4];
+    float2 v[4][8];
     #pragma unroll
-    for (int b = 0; b < 2; b++) {
-        float2 f[4];
-        grid3_levels<4, true>(g, 8 * HALF + 4 * b, ux, uy, uz, f);
-        const uint4 hi = make_uint4(pack_h2(f[0].x, f[0].y), pack_h2(f[1].x, f[1].y), pack_h2(f[2].x, f[2].y), pack_h2(f[3].x, f[3].y));
-        *reinterpret_cast<uint4*>(F + sw128(row, 2 * HALF + b)) = hi;
-        *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * HALF + b)) =
-            make_uint4(pack_h2(h_resid(f[0].x), h_resid(f[0].y)), pack_h2(h_resid(f[1].x), h_resid(f[1].y)),
-                       pack_h2(h_resid(f[2].x), h_resid(f[2].y)), pack_h2(h_resid(f[3].x), h_resid(f[3].y)));
-        if (hi_out) hi_out[b] = hi;
+    for (int i = 0; i < 4; i++) {
+        const int l = l0 + i;
+        const float scale = g.lv.scale[l];
+        float px = __fmaf_rn(x, scale, 0.5f), py = __fmaf_rn(y, scale, 0.5f), pz = __fmaf_rn(z, scale, 0.5f);
+        const uint32_t gx = (uint32_t)floorf(px), gy = (uint32_t)floorf(py), gz = (uint32_t)floorf(pz);
+        px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy); pz = __fsub_rn(pz, (float)gz);
+        if (g.interp == 1) { px = smooth_(px); py = smooth_(py); pz = smooth_(pz); }
+        fx[i] = px; fy[i] = py; fz[i] = pz;
+        const float2* __restrict__ tab = g.lbase[l];
+        const uint32_t mask = g.lv.mask[l], sy = g.lv.sy[l], sz = g.lv.sz[l];
+        const bool hashed = g.lv.hashed[l] != 0;
+        const bool has_z = hashed || sz != 0;
+        uint32_t idx[8];
+        if (hashed) {
+            const uint32_t y0 = gy * HASH_P1, y1 = y0 + HASH_P1, z0 = gz * HASH_P2, z1 = z0 + HASH_P2;
+            idx[0] = gx ^ y0 ^ z0; idx[1] = (gx + 1) ^ y0 ^ z0; idx[2] = gx ^ y1 ^ z0; idx[3] = (gx + 1) ^ y1 ^ z0;
+            idx[4] = gx ^ y0 ^ z1; idx[5] = (gx + 1) ^ y0 ^ z1; idx[6] = gx ^ y1 ^ z1; idx[7] = (gx + 1) ^ y1 ^ z1;
+        } else {
+            const uint32_t b = gx + gy * sy + gz * sz;
+            idx[0] = b; idx[1] = b + 1; idx[2] = b + sy; idx[3] = b + sy + 1;
+            idx[4] = b + sz; idx[5] = b + sz + 1; idx[6] = b + sz + sy; idx[7] = b + sz + sy + 1;
+        }
+        #pragma unroll
+        for (int c = 0; c < 4; c++) v[i][c] = __ldg(tab + (idx[c] & mask));
+        #pragma unroll
+        for (int c = 4; c < 8; c++) v[i][c] = has_z ? __ldg(tab + (idx[c] & mask)) : make_float2(0.f, 0.f);
+        if (!has_z) fz[i] = 0.f;
+    }
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float px = fx[i], py = fy[i], pz = fz[i];
+        const float qx = 1.0f - px, qy = 1.0f - py;
+        const float w00 = qx * qy, w10 = px * qy, w01 = qx * py, w11 = px * py;
+        const float a0 = fmaf(w11, v[i][3].x, fmaf(w01, v[i][2].x, fmaf(w10, v[i][1].x, w00 * v[i][0].x)));
+        const float a1 = fmaf(w11, v[i][3].y, fmaf(w01, v[i][2].y, fmaf(w10, v[i][1].y, w00 * v[i][0].y)));
+        const float b0 = fmaf(w11, v[i][7].x, fmaf(w01, v[i][6].x, fmaf(w10, v[i][5].x, w00 * v[i][4].x)));
+        const float b1 = fmaf(w11, v[i][7].y, fmaf(w01, v[i][6].y, fmaf(w10, v[i][5].y, w00 * v[i][4].y)));
+        out[i] = make_float2(fmaf(pz, b0 - a0, a0), fmaf(pz, b1 - a1, a1));
+    }
+}
+
+// 2-D ambient grid, 8 consecutive levels from l0 (32 gathers in flight)
+__device__ __forceinline__ void gather2_dyn8(const GridDesc& g, int l0, float x, float y, float2 (&out)[8]) {
+    const bool oob = x < 0 || x > 1 || y < 0 || y > 1;            // tanh output mapped to [0,1]: cannot happen, kept for safety
+    if (oob) { x = 0.5f; y = 0.5f; }
+    float fx[8], fy[8];
+    float2 v[8][4];
+    #pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int l = l0 + i;
+        const float scale = g.lv.scale[l];
+        float px = __fmaf_rn(x, scale, 0.5f), py = __fmaf_rn(y, scale, 0.5f);
+        const uint32_t gx = (uint32_t)floorf(px), gy = (uint32_t)floorf(py);
+        px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy);
+        if (g.interp == 1) { px = smooth_(px); py = smooth_(py); }
+        fx[i] = px; fy[i] = py;
+        const float2* __restrict__ tab = g.lbase[l];
+        const uint32_t mask = g.lv.mask[l], sy = g.lv.sy[l];
+        uint32_t idx[4];
+        if (g.lv.hashed[l]) {
+            const uint32_t y0 = gy * HASH_P1, y1 = y0 + HASH_P1;
+            idx[0] = gx ^ y0; idx[1] = (gx + 1) ^ y0; idx[2] = gx ^ y1; idx[3] = (gx + 1) ^ y1;
+        } else {
+            const uint32_t b = gx + gy * sy;
+            idx[0] = b; idx[1] = b + 1; idx[2] = b + sy; idx[3] = b + sy + 1;
+        }
+        #pragma unroll
+        for (int c = 0; c < 4; c++) v[i][c] = __ldg(tab + (idx[c] & mask));
+    }
+    #pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float px = fx[i], py = fy[i], qx = 1.0f - px, qy = 1.0f - py;
+        const float w00 = qx * qy, w10 = px * qy, w01 = qx * py, w11 = px * py;
+        const float a0 = fmaf(w11, v[i][3].x, fmaf(w01, v[i][2].x, fmaf(w10, v[i][1].x, w00 * v[i][0].x)));
+        const float a1 = fmaf(w11, v[i][3].y, fmaf(w01, v[i][2].y, fmaf(w10, v[i][1].y, w00 * v[i][0].y)));
+        out[i] = oob ? make_float2(0.f, 0.f) : make_float2(a0, a1);
     }
 }
 
@@ -184,15 +261,26 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
                 if (a.io.pos4) { const float4 p = a.io.pos4[i]; x = p.x; y = p.y; z = p.z; }
                 else { x = a.io.xyzs[3 * (size_t)i]; y = a.io.xyzs[3 * (size_t)i + 1]; z = a.io.xyzs[3 * (size_t)i + 2]; }
             }
-            const float ux = valid ? (x + a.bound) * a.inv2b : 0.5f, uy = (y + a.bound) * a.inv2b, uz = (z + a.bound) * a.inv2b;
+            float ux = (x + a.bound) * a.inv2b, uy = (y + a.bound) * a.inv2b, uz = (z + a.bound) * a.inv2b;
+            // out-of-range inputs encode to 0 (gridencoder.cu:110-135): sample the centre, zero the result
+            const bool oob = ux < 0 || ux > 1 || uy < 0 || uy > 1 || uz < 0 || uz > 1;
+            if (oob) { ux = 0.5f; uy = 0.5f; uz = 0.5f; }
             mbar_wait(bar_empty + 8 * slot, (n & 1) ^ 1);                 // slot released by the consumer of its previous use
             uint8_t* F = smem + L::F + slot * SP_TILE_BYTES;
-            uint4 hi[2];
-            if (half == 0) produce_pos<0>(a.grid, ux, uy, uz, F, row, hi);
-            else produce_pos<1>(a.grid, ux, uy, uz, F, row, hi);
-            if (valid) {
-                a.io.feat_hi[(size_t)i * 4 + 2 * half] = hi[0];
-                a.io.feat_hi[(size_t)i * 4 + 2 * half + 1] = hi[1];
+            // this thread's levels: 4u .. 4u+3 for units u = half and half + 2 (balances the 8-corner coarse levels
+            // and the 4-corner z-dropped fine levels between the two threads of a row)
+            #pragma unroll 1
+            for (uint32_t b = 0; b < 2; b++) {
+                const uint32_t u = half + 2 * b;
+                float2 f[4];
+                gather3_dyn4(a.grid, 4 * u, ux, uy, uz, f);
+                if (oob) { f[0] = f[1] = f[2] = f[3] = make_float2(0.f, 0.f); }
+                const uint4 hi = make_uint4(pack_h2(f[0].x, f[0].y), pack_h2(f[1].x, f[1].y), pack_h2(f[2].x, f[2].y), pack_h2(f[3].x, f[3].y));
+                *reinterpret_cast<uint4*>(F + sw128(row, u)) = hi;
+                *reinterpret_cast<uint4*>(F + sw128(row, 4 + u)) =
+                    make_uint4(pack_h2(h_resid(f[0].x), h_resid(f[0].y)), pack_h2(h_resid(f[1].x), h_resid(f[1].y)),
+                               pack_h2(h_resid(f[2].x), h_resid(f[2].y)), pack_h2(h_resid(f[3].x), h_resid(f[3].y)));
+                if (valid) a.io.feat_hi[(size_t)i * 4 + u] = hi;
             }
             fence_async_smem();
             mbar_arrive(bar_full + 8 * slot);
@@ -248,7 +336,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             tc_fence_after();
             // ambient output layer (128 -> 2) in fp32 from the accumulator, weights from the constant bank; tanh
             float s0 = 0.f, s1 = 0.f;
-            #pragma unroll
+            #pragma unroll 1
             for (int c = 0; c < 4; c++) {
                 float v[32];
                 tmem_ld32(t_d + 32 * c, v);
@@ -275,17 +363,6 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
 // ======================================================================================================================
 // kernel B: features + 2-D gather -> sigma / colour
 // ======================================================================================================================
-template <int HALF>
-__device__ __forceinline__ void produce_amb(const GridDesc& g, float vx, float vy, uint8_t* F, uint32_t row) {
-    float2 f[8];
-    grid2_levels<8>(g, 8 * HALF, vx, vy, f);
-    #pragma unroll
-    for (int u = 0; u < 2; u++)
-        *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * HALF + u)) =
-            make_uint4(pack_h2(f[4 * u].x, f[4 * u].y), pack_h2(f[4 * u + 1].x, f[4 * u + 1].y),
-                       pack_h2(f[4 * u + 2].x, f[4 * u + 2].y), pack_h2(f[4 * u + 3].x, f[4 * u + 3].y));
-}
-
 __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
     using L = SpSmem<WB2_TOTAL>;
     extern __shared__ uint8_t smem_raw[];
@@ -319,8 +396,13 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             uint8_t* F = smem + L::F + slot * SP_TILE_BYTES;
             *reinterpret_cast<uint4*>(F + sw128(row, 2 * half)) = hi0;
             *reinterpret_cast<uint4*>(F + sw128(row, 2 * half + 1)) = hi1;
-            if (half == 0) produce_amb<0>(a.grid, vx, vy, F, row);
-            else produce_amb<1>(a.grid, vx, vy, F, row);
+            float2 f[8];
+            gather2_dyn8(a.grid, 8 * half, vx, vy, f);
+            #pragma unroll
+            for (int u = 0; u < 2; u++)
+                *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * half + u)) =
+                    make_uint4(pack_h2(f[4 * u].x, f[4 * u].y), pack_h2(f[4 * u + 1].x, f[4 * u + 1].y),
+                               pack_h2(f[4 * u + 2].x, f[4 * u + 2].y), pack_h2(f[4 * u + 3].x, f[4 * u + 3].y));
             fence_async_smem();
             mbar_arrive(bar_full + 8 * slot);
         }

@@ -207,32 +207,35 @@ __global__ void __launch_bounds__(128) k_march_chunk(MarchArgs a, RayState st, S
         Probe p;
         while (count < budget && march_next(m, r, far, t, p)) { count++; t = __fadd_rn(t, p.dt); }
     }
-    // warp-aggregated allocation of `count` slots
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t incl = count;
+    // warp-aggregated allocation of `count` slots.  Layout inside the warp's block: SLOT-MAJOR across the warp's 32 rays
+    // (slot k of every ray that has one, then slot k+1, ...), dense.  The 32 rays of a warp are 32 neighbouring pixels of an
+    // image row, so 32 consecutive samples of the list lie side by side in space: the field kernels' grid gathers of one
+    // warp then share cache lines instead of touching 32 different ones (consecutive samples of ONE ray are a whole step apart).
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    uint32_t warp_total = count, warp_max = count;
     #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (uint32_t)o) incl += u;
+    for (int o = 16; o > 0; o >>= 1) {
+        warp_total += __shfl_xor_sync(0xffffffffu, warp_total, o);
+        warp_max = max(warp_max, __shfl_xor_sync(0xffffffffu, warp_max, o));
     }
-    const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
     uint32_t base = 0;
-    if (lane == 31 && warp_total) base = atomicAdd(ctl + CTL_TOTAL, warp_total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    if (!active) return;
-    const uint32_t off = base + incl - count;
-    st.seg_off[n] = off;
-    st.seg_cnt[n] = count;
-    if (count == 0) return;
+    if (lane == 0 && warp_total) base = atomicAdd(ctl + CTL_TOTAL, warp_total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (active) { st.seg_off[n] = base; st.seg_cnt[n] = count; }
     float t = t0;
-    Probe p;
-    uint32_t step = 0;
-    while (step < count && march_next(m, r, far, t, p)) {
-        t = __fadd_rn(t, p.dt);
-        sb.pos4[off + step] = make_float4(p.x, p.y, p.z, __int_as_float((int)n));
-        sb.dl[off + step] = make_float2(p.dt, t);
-        if (sb.occ_index) sb.occ_index[off + step] = p.index;
-        step++;
+    uint32_t off = base;
+    for (uint32_t k = 0; k < warp_max; k++) {
+        const uint32_t have = __ballot_sync(0xffffffffu, k < count);
+        if (k < count) {
+            Probe p;
+            march_next(m, r, far, t, p);               // succeeds: the counting pass took the same steps
+            t = __fadd_rn(t, p.dt);
+            const uint32_t idx = off + __popc(have & lt);
+            sb.pos4[idx] = make_float4(p.x, p.y, p.z, __int_as_float((int)n));
+            sb.dl[idx] = make_float2(p.dt, t);
+            if (sb.occ_index) sb.occ_index[idx] = p.index;
+        }
+        off += __popc(have);
     }
 }
 
@@ -242,28 +245,43 @@ __global__ void __launch_bounds__(128) k_march_chunk(MarchArgs a, RayState st, S
 __global__ void __launch_bounds__(128) k_composite_chunk(CompArgs a, RayState st, SampleBuf sb, uint32_t* __restrict__ ctl) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t budget = a.budget_from_ctl ? ctl[CTL_EXTRA] : a.budget;
-    if (budget == 0 || n >= a.N || !st.alive[n]) return;
-    const uint32_t off = st.seg_off[n], cnt = st.seg_cnt[n];
-    float weight_sum = st.wsum[n], d = st.depth[n];
-    float r = st.img[3 * (size_t)n], g = st.img[3 * (size_t)n + 1], b = st.img[3 * (size_t)n + 2];
-    float t = st.t[n];
+    if (budget == 0) return;
+    const bool active = n < a.N && st.alive[n];
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    const uint32_t cnt = active ? st.seg_cnt[n] : 0;
+    uint32_t off = active ? st.seg_off[n] : 0;                    // the warp's block (same value in every active lane)
+    uint32_t warp_max = cnt;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) warp_max = max(warp_max, __shfl_xor_sync(0xffffffffu, warp_max, o));
+    float weight_sum = 0.f, d = 0.f, r = 0.f, g = 0.f, b = 0.f, t = 0.f;
+    if (active) {
+        weight_sum = st.wsum[n]; d = st.depth[n];
+        r = st.img[3 * (size_t)n]; g = st.img[3 * (size_t)n + 1]; b = st.img[3 * (size_t)n + 2];
+        t = st.t[n];
+    }
     uint32_t step = 0;
     bool terminated = false;
-    while (step < cnt) {
-        const float4 o = sb.out4[off + step];          // sigma, r, g, b
-        const float2 dl = sb.dl[off + step];
-        const float alpha = 1.0f - __expf(-o.x * dl.x);
-        const float T = 1 - weight_sum;
-        const float weight = alpha * T;
-        weight_sum += weight;
-        t = dl.y;
-        d = fmaf(weight, t, d);
-        r = fmaf(weight, o.y, r);
-        g = fmaf(weight, o.z, g);
-        b = fmaf(weight, o.w, b);
-        if (T < a.T_thresh) { terminated = true; break; }
-        step++;
+    // slot-major walk of the warp's block (layout of k_march_chunk)
+    for (uint32_t k = 0; k < warp_max; k++) {
+        const uint32_t have = __ballot_sync(0xffffffffu, k < cnt);
+        if (k < cnt && !terminated) {
+            const uint32_t idx = off + __popc(have & lt);
+            const float4 o = sb.out4[idx];          // sigma, r, g, b
+            const float2 dl = sb.dl[idx];
+            const float alpha = 1.0f - __expf(-o.x * dl.x);
+            const float T = 1 - weight_sum;
+            const float weight = alpha * T;
+            weight_sum += weight;
+            t = dl.y;
+            d = fmaf(weight, t, d);
+            r = fmaf(weight, o.y, r);
+            g = fmaf(weight, o.z, g);
+            b = fmaf(weight, o.w, b);
+            if (T < a.T_thresh) terminated = true; else step++;
+        }
+        off += __popc(have);
     }
+    if (!active) return;
     // slots consumed this round: terminated at sample (step+1); ran dry at slot cnt+1 (delta == 0 terminator)
     const bool dead = terminated || cnt < budget;
     const uint32_t composited = terminated ? step + 1 : cnt;
