@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
             // ambient output layer (128 -> 2) in fp32 from the accumulator, weights from the constant bank; tanh
-            float s0 = 0.f, s1 = 0.f;
+            float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;          // (even, odd) column partial sums of the two outputs
             #pragma unroll 1
             for (int c = 0; c < 4; c++) {
                 float v[32];
@@ -345,12 +345,13 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
                     for (int q = 0; q < 32; q++) dbg[1 * 128 * 144 + 32 * c + q] = v[q];
                 }
                 #pragma unroll
-                for (int q = 0; q < 32; q++) {
-                    const float r = fmaxf(v[q], 0.f);
-                    s0 = fmaf(r, a.w_amb2[32 * c + q], s0);
-                    s1 = fmaf(r, a.w_amb2[128 + 32 * c + q], s1);
+                for (int q = 0; q < 32; q += 2) {
+                    const float2 r = make_float2(fmaxf(v[q], 0.f), fmaxf(v[q + 1], 0.f));
+                    acc0 = ffma2(r, make_float2(a.w_amb2[32 * c + q], a.w_amb2[32 * c + q + 1]), acc0);
+                    acc1 = ffma2(r, make_float2(a.w_amb2[128 + 32 * c + q], a.w_amb2[128 + 32 * c + q + 1]), acc1);
                 }
             }
+            const float s0 = acc0.x + acc0.y, s1 = acc1.x + acc1.y;
             if (dbg) { dbg[2 * 128 * 144 + 0] = s0; dbg[2 * 128 * 144 + 1] = s1; }
             if (i < M) a.io.amb_pos[i] = make_float2(tanhf(s0), tanhf(s1));
         }

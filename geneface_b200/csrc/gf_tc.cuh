@@ -108,8 +108,23 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 __device__ __forceinline__ float h_resid(float v) { return v - __half2float(__float2half_rn(v)); }   // the part fp16 drops
 
 
+// ReLU + fp16x2 pack in ONE instruction (cvt.relu): low half = max(lo, 0), high half = max(hi, 0)
+__device__ __forceinline__ uint32_t pack_relu_h2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// same, rounding toward zero: for v >= 0 the packed value never exceeds v, so the residual v - hi is >= 0
+__device__ __forceinline__ uint32_t pack_relu_rz_h2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t p) { return __half22float2(*reinterpret_cast<const __half2*>(&p)); }
+
 // NCHUNK x 32 accumulator columns starting at col0 (this thread's TMEM lane) -> (+bias) -> ReLU -> fp16 -> A operand region.
-// SPLIT: also emit the fp16 residual into a second A region (hi + lo ~ 22-bit operand).
+// SPLIT: also emit the fp16 residual into a second A region (hi + lo ~ 21-bit operand): hi = rz(relu(v)) so that the
+// residual relu(v) - hi is non-negative and a second cvt.relu packs it (a negative v gives hi = 0 and residual v -> 0).
 template <bool SPLIT, int NCHUNK>
 __device__ __forceinline__ void epilogue_relu_to_A_n(uint32_t t_d, uint32_t t_a, uint32_t t_alo, int col0, const float* __restrict__ bias_smem, float* dbg) {
     #pragma unroll 1
@@ -121,22 +136,43 @@ __device__ __forceinline__ void epilogue_relu_to_A_n(uint32_t t_d, uint32_t t_a,
             #pragma unroll
             for (int i = 0; i < 32; i++) dbg[col + i] = v[i];
         }
-        #pragma unroll
-        for (int i = 0; i < 32; i++) {
-            if (bias_smem) v[i] += bias_smem[col + i];
-            v[i] = fmaxf(v[i], 0.f);
+        if (bias_smem) {
+            #pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(bias_smem + col + i);
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            }
         }
         uint32_t p[16];
-        #pragma unroll
-        for (int i = 0; i < 16; i++) p[i] = pack_h2(v[2 * i], v[2 * i + 1]);
-        tmem_st16(t_a + (col >> 1), p);
         if (SPLIT) {
             #pragma unroll
-            for (int i = 0; i < 16; i++) p[i] = pack_h2(h_resid(v[2 * i]), h_resid(v[2 * i + 1]));
+            for (int i = 0; i < 16; i++) p[i] = pack_relu_rz_h2(v[2 * i], v[2 * i + 1]);
+            tmem_st16(t_a + (col >> 1), p);
+            #pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const float2 h = unpack_h2(p[i]);
+                p[i] = pack_relu_h2(v[2 * i] - h.x, v[2 * i + 1] - h.y);
+            }
             tmem_st16(t_alo + (col >> 1), p);
+        } else {
+            #pragma unroll
+            for (int i = 0; i < 16; i++) p[i] = pack_relu_h2(v[2 * i], v[2 * i + 1]);
+            tmem_st16(t_a + (col >> 1), p);
         }
     }
     tmem_wait_st();
+}
+
+// packed fp32 FMA (Blackwell FFMA2): d = a * b + c on two lanes
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    uint64_t ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
 }
 
 }  // namespace gf
