@@ -52,7 +52,8 @@ static_assert(WB2_MRG % 1024 == 0 && WB2_COL1 % 1024 == 0 && WB2_SH % 1024 == 0,
 template <uint32_t W>
 struct SpSmem {
     static constexpr uint32_t F = W;
-    static constexpr uint32_t BIAS = F + SP_NSLOT * SP_TILE_BYTES;   // 128 floats
+    static constexpr uint32_t DIR = F + SP_NSLOT * SP_TILE_BYTES;    // per slot: 128 x float4 view directions (kernel B)
+    static constexpr uint32_t BIAS = DIR + SP_NSLOT * 128 * 16;      // 128 floats
     static constexpr uint32_t BAR = BIAS + 512;                      // wbar, full[NSLOT], empty[NSLOT], mma[2]
     static constexpr uint32_t TMEM = BAR + 8 * (1 + 2 * SP_NSLOT + 2);
     static constexpr uint32_t TOTAL = TMEM + 16;
@@ -152,6 +153,8 @@ __device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, cons
 // 3-D position grid, 4 consecutive levels from l0.  Levels whose index drops z (gridencoder.cu:72 quirk) or are dense fetch the
 // z+1 plane only when it exists.  Interpolation is bilinear per z-plane, then a lerp in z (the fp32 result differs from the
 // reference's corner-order sum by rounding only; it is rounded to fp16 right after).
+// ALLFLAT: every level of the batch drops z and is not hashed -> only the 4 corners of the z0 plane exist (uniform fast path).
+template <bool ALLFLAT>
 __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x, float y, float z, float2 (&out)[4]) {
     float fx[4], fy[4], fz[4];
     float2 v[4][8];
@@ -166,10 +169,14 @@ __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x,
         fx[i] = px; fy[i] = py; fz[i] = pz;
         const float2* __restrict__ tab = g.lbase[l];
         const uint32_t mask = g.lv.mask[l], sy = g.lv.sy[l], sz = g.lv.sz[l];
-        const bool hashed = g.lv.hashed[l] != 0;
-        const bool has_z = hashed || sz != 0;
+        const bool hashed = !ALLFLAT && g.lv.hashed[l] != 0;
+        const bool has_z = !ALLFLAT && (hashed || sz != 0);
         uint32_t idx[8];
-        if (hashed) {
+        if (ALLFLAT) {
+            const uint32_t b = gx + gy * sy;
+            idx[0] = b; idx[1] = b + 1; idx[2] = b + sy; idx[3] = b + sy + 1;
+            idx[4] = idx[5] = idx[6] = idx[7] = 0;
+        } else if (hashed) {
             const uint32_t y0 = gy * HASH_P1, y1 = y0 + HASH_P1, z0 = gz * HASH_P2, z1 = z0 + HASH_P2;
             idx[0] = gx ^ y0 ^ z0; idx[1] = (gx + 1) ^ y0 ^ z0; idx[2] = gx ^ y1 ^ z0; idx[3] = (gx + 1) ^ y1 ^ z0;
             idx[4] = gx ^ y0 ^ z1; idx[5] = (gx + 1) ^ y0 ^ z1; idx[6] = gx ^ y1 ^ z1; idx[7] = (gx + 1) ^ y1 ^ z1;
@@ -180,9 +187,11 @@ __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x,
         }
         #pragma unroll
         for (int c = 0; c < 4; c++) v[i][c] = __ldg(tab + (idx[c] & mask));
-        #pragma unroll
-        for (int c = 4; c < 8; c++) v[i][c] = has_z ? __ldg(tab + (idx[c] & mask)) : make_float2(0.f, 0.f);
-        if (!has_z) fz[i] = 0.f;
+        if (!ALLFLAT) {
+            #pragma unroll
+            for (int c = 4; c < 8; c++) v[i][c] = has_z ? __ldg(tab + (idx[c] & mask)) : make_float2(0.f, 0.f);
+            if (!has_z) fz[i] = 0.f;
+        }
     }
     #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -191,6 +200,7 @@ __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x,
         const float w00 = qx * qy, w10 = px * qy, w01 = qx * py, w11 = px * py;
         const float a0 = fmaf(w11, v[i][3].x, fmaf(w01, v[i][2].x, fmaf(w10, v[i][1].x, w00 * v[i][0].x)));
         const float a1 = fmaf(w11, v[i][3].y, fmaf(w01, v[i][2].y, fmaf(w10, v[i][1].y, w00 * v[i][0].y)));
+        if (ALLFLAT) { out[i] = make_float2(a0, a1); continue; }
         const float b0 = fmaf(w11, v[i][7].x, fmaf(w01, v[i][6].x, fmaf(w10, v[i][5].x, w00 * v[i][4].x)));
         const float b1 = fmaf(w11, v[i][7].y, fmaf(w01, v[i][6].y, fmaf(w10, v[i][5].y, w00 * v[i][4].y)));
         out[i] = make_float2(fmaf(pz, b0 - a0, a0), fmaf(pz, b1 - a1, a1));
@@ -235,6 +245,7 @@ __device__ __forceinline__ void gather2_dyn8(const GridDesc& g, int l0, float x,
     }
 }
 
+template <bool DBG>
 __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
     using L = SpSmem<WA_TOTAL>;
     extern __shared__ uint8_t smem_raw[];
@@ -252,6 +263,15 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
     if (warp < 8) {
         // ------------------------------------------------ producers ------------------------------------------------
         const uint32_t half = tid >> 7, row = tid & 127;
+        uint32_t flat_units = 0;          // bit u: levels 4u..4u+3 all drop z and are not hashed
+        #pragma unroll
+        for (int u = 0; u < 4; u++) {
+            bool flat = true;
+            #pragma unroll
+            for (int q = 0; q < 4; q++) flat = flat && a.grid.lv.sz[4 * u + q] == 0 && a.grid.lv.hashed[4 * u + q] == 0;
+            flat_units |= (flat ? 1u : 0u) << u;
+        }
+        #pragma unroll 1
         for (uint32_t j = 0; j < my_tiles; j++) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
             const uint32_t i = tile * 128 + row;
@@ -273,7 +293,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             for (uint32_t b = 0; b < 2; b++) {
                 const uint32_t u = half + 2 * b;
                 float2 f[4];
-                gather3_dyn4(a.grid, 4 * u, ux, uy, uz, f);
+                if ((flat_units >> u) & 1) gather3_dyn4<true>(a.grid, 4 * u, ux, uy, uz, f);
+                else gather3_dyn4<false>(a.grid, 4 * u, ux, uy, uz, f);
                 if (oob) { f[0] = f[1] = f[2] = f[3] = make_float2(0.f, 0.f); }
                 const uint4 hi = make_uint4(pack_h2(f[0].x, f[0].y), pack_h2(f[1].x, f[1].y), pack_h2(f[2].x, f[2].y), pack_h2(f[3].x, f[3].y));
                 *reinterpret_cast<uint4*>(F + sw128(row, u)) = hi;
@@ -297,7 +318,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
         for (uint32_t j = stream; j < my_tiles; j += 2) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
             const uint32_t i = tile * 128 + row;
-            float* dbg = (a.dbg && tile == 0) ? a.dbg + (size_t)row * 144 : nullptr;
+            float* dbg = (DBG && a.dbg && tile == 0) ? a.dbg + (size_t)row * 144 : nullptr;   // DBG = false: folds every dump away
             const uint32_t f_addr = sbase + L::F + slot * SP_TILE_BYTES;
             tc_fence_before();
             bar_named(1 + stream, 128);                                   // previous tile's accumulator reads are done
@@ -364,6 +385,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
 // ======================================================================================================================
 // kernel B: features + 2-D gather -> sigma / colour
 // ======================================================================================================================
+template <bool DBG>
 __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
     using L = SpSmem<WB2_TOTAL>;
     extern __shared__ uint8_t smem_raw[];
@@ -381,22 +403,40 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
     if (warp < 8) {
         // ------------------------------------------------ producers ------------------------------------------------
         const uint32_t half = tid >> 7, row = tid & 127;
-        for (uint32_t j = 0; j < my_tiles; j++) {
-            const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
-            const uint32_t i = tile * 128 + row;
-            const bool valid = i < M;
-            uint4 hi0 = make_uint4(0, 0, 0, 0), hi1 = hi0;
-            float2 ap = make_float2(0.f, 0.f);
-            if (valid) {
-                hi0 = a.io.feat_hi[(size_t)i * 4 + 2 * half];
-                hi1 = a.io.feat_hi[(size_t)i * 4 + 2 * half + 1];
-                ap = a.io.amb_pos[i];
+        // per-row inputs of one tile; fetched ONE TILE AHEAD so that their DRAM latency overlaps the previous tile's gathers
+        struct RowIn { uint4 hi0, hi1; float2 ap; float4 dir; };
+        auto fetch = [&](uint32_t j) {
+            RowIn r;
+            r.hi0 = make_uint4(0, 0, 0, 0); r.hi1 = r.hi0; r.ap = make_float2(0.f, 0.f); r.dir = make_float4(0.f, 0.f, 1.f, 0.f);
+            const uint32_t i = (blockIdx.x + j * gridDim.x) * 128 + row;
+            if (j < my_tiles && i < M) {
+                r.hi0 = a.io.feat_hi[(size_t)i * 4 + 2 * half];
+                r.hi1 = a.io.feat_hi[(size_t)i * 4 + 2 * half + 1];
+                r.ap = a.io.amb_pos[i];
+                if (half == 1) {          // view direction of the row's ray: fetched here, off the consumers' critical path
+                    if (a.io.pos4) {
+                        const int ray = __float_as_int(a.io.pos4[i].w);
+                        r.dir.x = __ldg(a.io.rays_d + 3 * (size_t)ray); r.dir.y = __ldg(a.io.rays_d + 3 * (size_t)ray + 1); r.dir.z = __ldg(a.io.rays_d + 3 * (size_t)ray + 2);
+                    } else { r.dir.x = a.io.dirs[3 * (size_t)i]; r.dir.y = a.io.dirs[3 * (size_t)i + 1]; r.dir.z = a.io.dirs[3 * (size_t)i + 2]; }
+                }
             }
+            return r;
+        };
+        RowIn nxt = fetch(0);
+        #pragma unroll 1
+        for (uint32_t j = 0; j < my_tiles; j++) {
+            const uint32_t slot = j % SP_NSLOT, n = j / SP_NSLOT;
+            const RowIn cur = nxt;
+            nxt = fetch(j + 1);
+            const uint4 hi0 = cur.hi0, hi1 = cur.hi1;
+            const float2 ap = cur.ap;
+            const float4 dir = cur.dir;
             const float vx = (ap.x + 1.0f) * 0.5f, vy = (ap.y + 1.0f) * 0.5f;
             mbar_wait(bar_empty + 8 * slot, (n & 1) ^ 1);
             uint8_t* F = smem + L::F + slot * SP_TILE_BYTES;
             *reinterpret_cast<uint4*>(F + sw128(row, 2 * half)) = hi0;
             *reinterpret_cast<uint4*>(F + sw128(row, 2 * half + 1)) = hi1;
+            if (half == 1) reinterpret_cast<float4*>(smem + L::DIR)[slot * 128 + row] = dir;
             float2 f[8];
             gather2_dyn8(a.grid, 8 * half, vx, vy, f);
             #pragma unroll
@@ -421,17 +461,9 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
             const uint32_t i = tile * 128 + row;
             const bool valid = i < M;
-            float* dbg = (a.dbg && tile == 0) ? a.dbg + (size_t)row * 144 : nullptr;
+            float* dbg = (DBG && a.dbg && tile == 0) ? a.dbg + (size_t)row * 144 : nullptr;   // DBG = false: folds every dump away
             uint8_t* F = smem + L::F + slot * SP_TILE_BYTES;
             const uint32_t f_addr = sbase + L::F + slot * SP_TILE_BYTES;
-            // view direction of this row's ray (for the SH K-extension of the colour layer)
-            float dx = 0.f, dy = 0.f, dz = 1.f;
-            if (valid) {
-                if (a.io.pos4) {
-                    const int ray = __float_as_int(a.io.pos4[i].w);
-                    dx = __ldg(a.io.rays_d + 3 * (size_t)ray); dy = __ldg(a.io.rays_d + 3 * (size_t)ray + 1); dz = __ldg(a.io.rays_d + 3 * (size_t)ray + 2);
-                } else { dx = a.io.dirs[3 * (size_t)i]; dy = a.io.dirs[3 * (size_t)i + 1]; dz = a.io.dirs[3 * (size_t)i + 2]; }
-            }
             tc_fence_before();
             bar_named(1 + stream, 128);
             // ---- sigma layer 0: D = F[:, 0:64] @ Ws0^T ------------------------------------------------------------
@@ -444,7 +476,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             }
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
-            epilogue_relu_to_A_n<false, 4>(t_d, t_a, 0, 0, nullptr, dbg ? dbg + 3 * 128 * 144 : nullptr);
+            epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 3 * 128 * 144 : nullptr);
             tc_fence_before();
             bar_named(1 + stream, 128);
             // ---- sigma layer 1 -----------------------------------------------------------------------------------------
@@ -457,8 +489,9 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             }
             // SH(dir) -> F[row][k 32..47]: the sigma-layer-0 MMA that read this slot has completed (waited above)
             {
+                const float4 dir = reinterpret_cast<const float4*>(smem + L::DIR)[slot * 128 + row];   // visible: the leader's full-barrier wait + bar.sync
                 float sh[16];
-                sh4(dx, dy, dz, sh);
+                sh4(dir.x, dir.y, dir.z, sh);
                 uint32_t p[8];
                 #pragma unroll
                 for (int q = 0; q < 8; q++) p[q] = pack_h2(sh[2 * q], sh[2 * q + 1]);
@@ -468,7 +501,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             }
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
-            epilogue_relu_to_A_n<false, 4>(t_d, t_a, 0, 0, nullptr, dbg ? dbg + 4 * 128 * 144 : nullptr);
+            epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 4 * 128 * 144 : nullptr);
             tc_fence_before();
             bar_named(1 + stream, 128);
             // ---- merged sigma layer 2 x colour layer 0 (N = 144) + SH part (SS, K = 16, N = 128) --------------------------
@@ -486,7 +519,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             float sg[4];
             tmem_ld4(t_d + 128, sg);
             if (dbg) dbg[5 * 128 * 144 + 128] = sg[0];
-            epilogue_relu_to_A_n<false, 4>(t_d, t_a, 0, 0, a.bias ? bias_ind : nullptr, dbg ? dbg + 5 * 128 * 144 : nullptr);
+            if (a.bias) epilogue_relu_to_A_pipe<true>(t_d, t_a, bias_ind, dbg ? dbg + 5 * 128 * 144 : nullptr);
+            else epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 5 * 128 * 144 : nullptr);
             tc_fence_before();
             bar_named(1 + stream, 128);
             // ---- colour layer 1 (N = 16; 3 real outputs) -> sigmoid ---------------------------------------------------------
@@ -539,8 +573,10 @@ static int ensure_split_pack(GfModel* m, cudaStream_t st) {
     k_tc_pack_split<<<(144 * 128 + 255) / 256, 256, 0, st>>>(s, img, img + WA_TOTAL);
     int rc = check_launch("tc split pack");
     if (rc) { cudaFree(img); return rc; }
-    if (cudaFuncSetAttribute(k_tc_amb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_tc_sigcol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_tc_amb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_amb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_sigcol<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_sigcol<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
         cudaMemcpyAsync(m->w_amb2_host, m->w + m->dev.a_w2, sizeof(float) * 256, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) {
         cudaGetLastError();
@@ -583,13 +619,15 @@ int field_tc_split_launch(const GfModel* model, const FieldTcIO& io_in, cudaStre
     a.wimg = (const uint8_t*)m->tc2_blob;
     a.bias = io.bias_amb;
     memcpy(a.w_amb2, m->w_amb2_host, sizeof(a.w_amb2));
-    k_tc_amb<<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
+    if (a.dbg) k_tc_amb<true><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
+    else k_tc_amb<false><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
     rc = check_launch("field_tc_split(amb)");
     if (rc) return rc;
     a.grid = model->dev.amb;
     a.wimg = (const uint8_t*)m->tc2_blob + WA_TOTAL;
     a.bias = model->dev.ind ? model->dev.w + model->dev.c_bind : nullptr;
-    k_tc_sigcol<<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
+    if (a.dbg) k_tc_sigcol<true><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
+    else k_tc_sigcol<false><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
     return check_launch("field_tc_split(sigcol)");
 }
 

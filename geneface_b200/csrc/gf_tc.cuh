@@ -163,6 +163,57 @@ __device__ __forceinline__ void epilogue_relu_to_A_n(uint32_t t_d, uint32_t t_a,
     tmem_wait_st();
 }
 
+// asynchronous 32-column accumulator load + the matching wait.  The wait names the destination registers as in/out operands so
+// that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                   "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]),
+                   "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),
+                   "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// 128 accumulator columns -> (+bias) -> ReLU -> fp16 A operand, software-pipelined: the load of chunk c+1 is in flight while
+// chunk c is converted and stored (this epilogue sits on the consumer streams' critical path).
+template <bool BIAS>
+__device__ __forceinline__ void epilogue_relu_to_A_pipe(uint32_t t_d, uint32_t t_a, const float* __restrict__ bias_smem, float* dbg) {
+    uint32_t r[2][32];
+    tmem_ld32_issue(t_d, r[0]);
+    tmem_wait_ld32(r[0]);
+    #pragma unroll
+    for (int c = 0; c < 4; c++) {
+        uint32_t (&cur)[32] = r[c & 1];
+        if (c < 3) tmem_ld32_issue(t_d + 32 * (c + 1), r[(c + 1) & 1]);
+        if (dbg) {
+            #pragma unroll
+            for (int i = 0; i < 32; i++) dbg[32 * c + i] = __uint_as_float(cur[i]);
+        }
+        uint32_t p[16];
+        #pragma unroll
+        for (int i = 0; i < 16; i++) {
+            float v0 = __uint_as_float(cur[2 * i]), v1 = __uint_as_float(cur[2 * i + 1]);
+            if (BIAS) { const float2 b = *reinterpret_cast<const float2*>(bias_smem + 32 * c + 2 * i); v0 += b.x; v1 += b.y; }
+            p[i] = pack_relu_h2(v0, v1);
+        }
+        tmem_st16(t_a + 16 * c, p);
+        if (c < 3) tmem_wait_ld32(r[(c + 1) & 1]);
+    }
+    tmem_wait_st();
+}
+
 // packed fp32 FMA (Blackwell FFMA2): d = a * b + c on two lanes
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     uint64_t ra, rb, rc, rd;
