@@ -317,12 +317,13 @@ def main():
                 "d2h_bytes_per_step": int(host_rgb8.numel())},
         "gpu_launches": launches * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": 236503296 if args.precision == "fp16" else None,   # dram read+write bytes per launch (= one 8.4 M-sample round), profiles/r01_summary.md
+                     "traffic": 1551318528 if args.precision == "fp16" else None,   # dram read+write bytes per 8.4 M-sample round (k_tc_amb + k_tc_sigcol), ncu capture in profiles/r01_summary.md
                      "algorithmic_bytes_per_launch": samples_per_frame // 4 * HEAD_SAMPLE_BYTES,
-                     "kernel": "k_field_tc" if args.precision == "fp16" else "k_field_fp32", "kernel_ms_per_frame": field_ms_per_frame,
+                     "kernel": "k_tc_amb+k_tc_sigcol" if args.precision == "fp16" else "k_field_fp32", "kernel_ms_per_frame": field_ms_per_frame,
                      "kernel_share_of_step": field_ms_per_frame / (ms_res / args.steps), "peak_source": peaks["source"],
                      "tensor_tflops": tflops, "tensor_frac_of_bf16_peak": tflops / peaks["bf16_tflops"],
-                     "note": "algorithmic gather bytes (1536 B/sample); the 16 MB tables are L2-resident so DRAM traffic is far below this"},
+                     "note": "algorithmic gather bytes (1536 B/sample: 16 levels x 8 corners x 8 B + 16 x 4 x 8 B); the 16 MB tables are L2-resident so DRAM traffic "
+                             "(sample lists + the 72 B/sample hand-off between the two field kernels) is far below this; one launch = one 8.4 M-sample round"},
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -545,3 +545,17 @@ def test_tc_field_and_frame_within_north_star_tolerance(head_model):
         ok, worst = close(a, b, rel=1e-3, abs_=1e-5)
         print(f"tc frame {k}: worst scaled err {worst:.2e}")
         assert ok, f"{k}: fp16 tensor-core frame deviates from fp32 by more than 1e-3 relative (worst {worst:.2e})"
+
+
+@pytest.mark.gpu
+def test_fused_single_kernel_mode_still_matches_oracle():
+    """GF_TC_MODE=fused selects the single-kernel tcgen05 field (field_tc.cu) instead of the default two-kernel pipeline.
+    The mode is latched at first use, so it runs in a child process: smoke() checks it against the CPU oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GF_TC_MODE="fused")
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "smoke ok" in r.stdout
