@@ -22,6 +22,12 @@ cpu_baseline: the CPU oracle (port of the reference path, OpenMP + numpy, all ho
 --impl reference: the reference's CPU implementation timed on the host cores (rank 0 only): the oracle port of the RAD-NeRF
          path on a bounded sample per step; the vanilla AD-NeRF (modules/nerfs) port is reported in `adnerf_cpu`.
 """
+import os as _os
+# The CPU legs alternate OpenMP regions (C oracle) and OpenBLAS GEMMs (numpy) ~10^3 times per frame sample.  With libgomp's default
+# ACTIVE wait policy its idle threads spin between regions and starve the BLAS threads (measured: 6 ms instead of 29 us per GEMM).
+# Must be set before libgomp is loaded, i.e. before torch/numpy are imported.
+_os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+_os.environ.setdefault("GOMP_SPINCOUNT", "0")
 import argparse
 import json
 import os
@@ -105,12 +111,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------ CPU legs
-def cpu_port_fps(n_rays=1024, threads=None):
-    """The CPU oracle (port of the reference RAD-NeRF path) on `n_rays` rays x 128 samples of the benchmark frame."""
+def host_threads():
+    """Threads for the CPU legs.  The port's host loop issues ~128 small numpy/OpenMP regions per frame sample; beyond a few dozen
+    threads their fork/join cost dominates (measured on the 128-core GPU host: 2048 rays took 280 s with 128 threads), so the legs
+    use min(cores, 32) and report that number."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get("GF_CPU_THREADS", "32"))))
+
+
+def _cpu_port_once(n_rays, threads):
     import numpy as np
     import torch
-    threads = threads or os.cpu_count()
-    os.environ["OMP_NUM_THREADS"] = str(threads)
+    from threadpoolctl import threadpool_limits
     torch.set_num_threads(threads)
     from geneface_b200 import synthetic
     from oracle import field as OF
@@ -122,17 +133,32 @@ def cpu_port_fps(n_rays=1024, threads=None):
     ro, rd = np.ascontiguousarray(ro[sel]), np.ascontiguousarray(rd[sel])
     fo = OF.FieldOracle(sd, bound=4.0)
     OF.MATMUL_DTYPE = np.float32          # timing leg: fp32 GEMMs like the reference's CPU tensors
-    t0 = time.perf_counter()
-    cf = OF.cal_cond_feat(sd, fi['cond'].numpy())
-    ws, depth, img, nears, fars, ns = OF.render_head(fo, sd, ro, rd, cf, sd['density_bitfield'], 3, 128, sd['aabb_infer'], hp['min_near'], 0.0, MAX_STEPS)
-    bgc = OF.get_bg_coords(H, W)[sel]
-    bg, _, _, _ = OF.render_torso_mix(OF.TorsoOracle(sd), sd, bgc, fi['poses6'].numpy(), fi['bg_color'][0].numpy()[sel], img, ws)
-    OF.finish(img, ws, depth, nears, fars, bg)
-    dt = time.perf_counter() - t0
+    with threadpool_limits(limits=threads):
+        t0 = time.perf_counter()
+        cf = OF.cal_cond_feat(sd, fi['cond'].numpy())
+        ws, depth, img, nears, fars, ns = OF.render_head(fo, sd, ro, rd, cf, sd['density_bitfield'], 3, 128, sd['aabb_infer'], hp['min_near'], 0.0, MAX_STEPS)
+        bgc = OF.get_bg_coords(H, W)[sel]
+        bg, _, _, _ = OF.render_torso_mix(OF.TorsoOracle(sd), sd, bgc, fi['poses6'].numpy(), fi['bg_color'][0].numpy()[sel], img, ws)
+        OF.finish(img, ws, depth, nears, fars, bg)
+        dt = time.perf_counter() - t0
     OF.MATMUL_DTYPE = np.float64
     assert int(ns.min()) == MAX_STEPS == int(ns.max())
+    return dt
+
+
+def cpu_port_fps(n_rays=None, threads=None, budget_s=12.0):
+    """The CPU oracle (port of the reference RAD-NeRF path) on a BOUNDED sample of the benchmark frame: `n_rays` rays x 128
+    samples (head + torso + mix).  n_rays=None: a 256-ray probe sizes the sample for about `budget_s` seconds of CPU work."""
+    threads = threads or host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    if n_rays is None:
+        _cpu_port_once(256, threads)                      # cold: library load, page faults
+        probe = _cpu_port_once(256, threads)
+        n_rays = int(min(16384, max(256, 256 * budget_s / max(probe, 1e-3))))
+        n_rays = 1 << (n_rays.bit_length() - 1)          # power of two
+    dt = _cpu_port_once(n_rays, threads)
     fps = 1.0 / (dt * (H * W) / n_rays)
-    return fps, dt, threads, f"{n_rays} of 262144 rays x 128 samples of the same frame (head+torso), {dt:.1f} s of CPU work, extrapolated"
+    return fps, dt, threads, f"{n_rays} of 262144 rays x 128 samples of the same frame (head+torso), {dt:.1f} s of CPU work on {threads} threads, extrapolated"
 
 
 def adnerf_cpu_fps(threads=None):
@@ -141,7 +167,7 @@ def adnerf_cpu_fps(threads=None):
         from oracle import adnerf_port
     except Exception as e:  # noqa: BLE001
         return {"unavailable": str(e)}
-    return adnerf_port.time_frame(threads or os.cpu_count())
+    return adnerf_port.time_frame(threads or host_threads())
 
 
 def run_reference_arm(args, rank):
@@ -149,19 +175,18 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     steps, warm = max(1, args.steps), args.warmup
-    n_rays = 2048
-    for _ in range(min(warm, 1)):
-        cpu_port_fps(n_rays)
     t0 = time.perf_counter()
+    fps, dt, threads, sample = cpu_port_fps(None, budget_s=10.0)      # warm-up step; also sizes the bounded sample
+    n_rays = int(sample.split()[0])
     fps_list = []
     for _ in range(steps):
         fps, dt, threads, sample = cpu_port_fps(n_rays)
         fps_list.append(fps)
-        if time.perf_counter() - t0 > 150:
+        if time.perf_counter() - t0 > 120:
             break
     k = len(fps_list)
     value = k / sum(1.0 / f for f in fps_list)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": k, "warmup": min(warm, 1),
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": k, "warmup": 1,
             "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "RAD-NeRF head+torso 512x512, 128 samples/ray (bound=4, all-ones bitfield); CPU port of the reference path",
                        "l2": "n/a (CPU)"},
@@ -181,6 +206,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("GF_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-may", action="store_true", help="skip the May-configuration context measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -327,19 +353,62 @@ def main():
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
-        fps, dt, threads, sample = cpu_port_fps(2048)
+        fps, dt, threads, sample = cpu_port_fps(None, budget_s=12.0)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample}
     if not args.no_ref_cuda and world == 1:
         try:
             line["reference_cuda"] = reference_cuda_fps(model, hp, fi, dev)
         except Exception as e:  # noqa: BLE001
             line["reference_cuda"] = {"unavailable": repr(e)[:200]}
+    if not args.no_may and world == 1:
+        try:
+            line["may_cfg"] = may_cfg_fps(dev, args.precision, not args.no_ref_cuda)
+        except Exception as e:  # noqa: BLE001
+            line["may_cfg"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def reference_cuda_fps(model, hp, fi, dev):
+def may_cfg_fps(dev, precision, with_ref):
+    """Context number (BASELINE.json configs[2]): the reference's own deployment configuration -- May head+torso, bound=1,
+    max_steps=16, dt_gamma=1/256, sphere occupancy -- rendered by the same fused path, beside the compiled reference loop."""
+    import torch
+    from geneface_b200 import synthetic
+    model, hp = synthetic.build_model(torso=True, bitfield='S', seed=0, device=dev)
+    fi = synthetic.frame_inputs(H, W, device=dev)
+    counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    out = {'rgb8': torch.empty(H * W, 3, dtype=torch.uint8, device=dev), 'counters': counters}
+    pose6 = fi['poses6']
+
+    def frame():
+        with torch.no_grad():
+            cf = model.cal_cond_feat(fi['cond'])
+            model.render_fused(cf, H, W, pose=fi['pose'][0], intrinsics=fi['intrinsics'], bg_color=fi['bg_color'], torso_pose=pose6,
+                               dt_gamma=hp['dt_gamma'], max_steps=hp['max_steps'], precision=precision, want=('rgb8', 'counters'), out=out)
+    for _ in range(5):
+        frame()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 40
+    e0.record()
+    for _ in range(n):
+        frame()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    c = counters.cpu().numpy()
+    res = {"value": 1000.0 / ms, "unit": "frames/s", "ms_per_frame": ms, "samples_per_frame": int(c[0]), "torso_pixels": int(c[1]),
+           "workload": "May cfg head+torso 512x512: bound=1, max_steps=%d, dt_gamma=1/256, sphere bitfield" % hp['max_steps']}
+    if with_ref:
+        try:
+            res["reference_cuda"] = reference_cuda_fps(model, hp, fi, dev, dt_gamma=hp['dt_gamma'], max_steps=hp['max_steps'])
+        except Exception as e:  # noqa: BLE001
+            res["reference_cuda"] = {"unavailable": repr(e)[:200]}
+    return res
+
+
+def reference_cuda_fps(model, hp, fi, dev, dt_gamma=0.0, max_steps=None):
     """Context number: the reference renderer assembled from the compiled UNMODIFIED reference kernels (oracle/_ref) on the
     same GPU and workload (the 'kernel to beat', BASELINE.md B-REF-CUDA).  Not part of the product path."""
     import torch
@@ -356,7 +425,7 @@ def reference_cuda_fps(model, hp, fi, dev):
         for it in range(4):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ws, depth, img, nears, fars, _ = ref.render_head(rays['rays_o'][0], rays['rays_d'][0], cf, 0.0, MAX_STEPS)
+            ws, depth, img, nears, fars, _ = ref.render_head(rays['rays_o'][0], rays['rays_d'][0], cf, dt_gamma, max_steps or MAX_STEPS)
             bg, _, _ = ref.torso_bg(bgc[0], fi['poses6'], fi['bg_color'][0])
             ref.finish(img, ws, depth, nears, fars, bg)
             e1.record()

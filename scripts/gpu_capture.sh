@@ -3,5 +3,5 @@
 mkdir -p gpurun_out
 P=${4:-fp16}
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:$1 -s ${2:-10} -c ${3:-1} -f -o gpurun_out/prof_$P \
-    python bench.py --steps 2 --warmup 3 --precision $P --no-cpu-baseline --no-ref-cuda > gpurun_out/ncu_full_$P.log 2>&1
+    python bench.py --steps 2 --warmup 3 --precision $P --no-cpu-baseline --no-ref-cuda --no-may > gpurun_out/ncu_full_$P.log 2>&1
 echo "full capture rc=$?"; tail -2 gpurun_out/ncu_full_$P.log; ls -la gpurun_out/*.ncu-rep
