@@ -256,15 +256,15 @@ def main():
             model.render_fused(cf, H, W, pose=poses[f], intrinsics=fi['intrinsics'], bg_color=bg, torso_pose=pose6_h[f], dt_gamma=0.0,
                                max_steps=MAX_STEPS, precision=args.precision, want=('rgb8', 'counters'), out=outbuf)
 
-    def frame_e2e(f):
-        with torch.no_grad():
-            cond_dv = conds_h[f].to(dev, non_blocking=True)        # H2D: the frame's condition window (pinned)
-            cf = model.cal_cond_feat(cond_dv)
-            p6 = convert_poses(poses_h[f][None])[0]                 # host; pose + pose6 travel by value in the launch
-            model.render_fused(cf, H, W, pose=poses_h[f], intrinsics=fi['intrinsics'], bg_color=bg, torso_pose=p6, dt_gamma=0.0,
-                               max_steps=MAX_STEPS, precision=args.precision, want=('rgb8', 'counters'), out=outbuf)
-            host_rgb8.copy_(rgb8, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the finished frame
+    # end to end = the public sequence API (geneface_b200.sequence.SequenceRenderer, the replacement of the frame loop of
+    # inference/nerfs/base_nerf_infer.py:131-179): per frame the condition window goes host->device from pinned memory, pose and
+    # pose6 travel by value in the launch, and the finished RGB8 frame goes device->host into a pinned ring; frames are pipelined
+    # (frame k+1 renders while frame k drains) and the call returns when every frame is resident in host memory.
+    seq = sequence.SequenceRenderer(model, H, W, fi['intrinsics'], precision=args.precision, max_steps=MAX_STEPS, dt_gamma=0.0, torso=True)
+    host_ring = torch.empty(args.steps, H, W, 3, dtype=torch.uint8).pin_memory()
+
+    def sequence_e2e():
+        seq.render(poses_h, conds_h, bg, args.warmup, args.warmup + args.steps, out_rgb8=host_ring)
 
     def barrier():
         if world > 1:
@@ -297,8 +297,7 @@ def main():
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for k in range(args.steps):
-        frame_e2e(args.warmup + k)
+    sequence_e2e()
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -340,7 +339,7 @@ def main():
                    "l2": "per-round sample lists (335 MB) exceed L2; the 16 MB grid tables are the algorithm's own hot set; no explicit flush",
                    "precision": args.precision, "samples_per_frame": samples_per_frame, "torso_pixels": torso_px, "s_total": s_total},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(conds_h[0].numel() * 4 + 16 * 4 + 6 * 4),
-                "d2h_bytes_per_step": int(host_rgb8.numel())},
+                "d2h_bytes_per_step": int(host_ring[0].numel()), "api": "geneface_b200.sequence.SequenceRenderer.render (pipelined frames)"},
         "gpu_launches": launches * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "traffic": 1551318528 if args.precision == "fp16" else None,   # dram read+write bytes per 8.4 M-sample round (k_tc_amb + k_tc_sigcol), ncu capture in profiles/r01_summary.md

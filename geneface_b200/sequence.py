@@ -50,7 +50,9 @@ class SequenceRenderer:
 
     @torch.no_grad()
     def render(self, poses, conds, bg_color, start, end, out_rgb8=None):
-        """poses [F,4,4], conds [F,smo,win,C] (device), bg_color [1,N,3]; returns uint8 [end-start, H, W, 3] pinned host tensor."""
+        """poses [F,4,4] (host or device), conds [F,smo,win,C] (device, or PINNED HOST: each frame's window is then copied host->device
+        asynchronously inside the loop), bg_color [1,N,3]; returns uint8 [end-start, H, W, 3] pinned host tensor.  Frames are pipelined:
+        frame k+1 is enqueued while frame k's RGB8 drains to the host ring on a copy stream; one synchronisation at the end."""
         from .utils import convert_poses
         n = end - start
         N = self.H * self.W
@@ -62,7 +64,10 @@ class SequenceRenderer:
             slot = k & 1
             if done[slot] is not None:
                 torch.cuda.current_stream().wait_event(done[slot])
-            cond_feat = self.model.cal_cond_feat(conds[f])
+            cond_f = conds[f]
+            if not cond_f.is_cuda:
+                cond_f = cond_f.to(dev_rgb8[0].device, non_blocking=True)
+            cond_feat = self.model.cal_cond_feat(cond_f)
             pose6 = convert_poses(poses[f:f + 1]) if self.torso else None
             self.model.render_fused(cond_feat, self.H, self.W, pose=poses[f], intrinsics=self.intrinsics, bg_color=bg_color, torso_pose=pose6,
                                     dt_gamma=self.dt_gamma, max_steps=self.max_steps, precision=self.precision, want=('rgb8',),

@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Train-step context benchmark (BASELINE.json configs[4], SURVEY.md section 8d "Config 5"): 4096 rays through
+march_rays_train -> field (grid encoders + torch MLPs) -> composite_rays_train, MSE loss, backward (composite backward,
+hash-grid backward, SH/freq backward) on the fine-grained ops of libgfrender.  Prints one JSON line with the step time and
+the per-kernel share (torch profiler).  Not part of bench.py's headline: training is the reference's secondary path.
+
+usage: python scripts/bench_train.py [--rays 4096] [--steps 20]
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rays", type=int, default=4096)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    args = ap.parse_args()
+    import torch
+    from geneface_b200 import synthetic, utils
+    assert torch.cuda.is_available(), "needs a GPU"
+    dev = torch.device("cuda", 0)
+    H = W = 512
+    model, hp = synthetic.build_model(torso=False, bitfield='S', seed=0, device=dev)
+    model.train()
+    fi = synthetic.frame_inputs(H, W, device=dev)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3)
+    g = torch.Generator(device=dev).manual_seed(3)
+    inds = torch.randint(0, H * W, [args.rays], device=dev, generator=g)
+    rays = utils.get_rays(fi['pose'], fi['intrinsics'], H, W)
+    rays_o, rays_d = rays['rays_o'][:, inds], rays['rays_d'][:, inds]
+    bgc = utils.get_bg_coords(H, W, dev)[:, inds]
+    target = torch.rand(1, args.rays, 3, device=dev, generator=g)
+    bg_color = fi['bg_color'][:, inds]
+
+    def step():
+        torch.manual_seed(4)                                   # perturb noise
+        opt.zero_grad(set_to_none=True)
+        out = model.render(rays_o, rays_d, fi['cond'], bgc, fi['poses6'], index=0, dt_gamma=hp['dt_gamma'], bg_color=bg_color, perturb=True,
+                           force_all_rays=False, max_steps=hp['max_steps'])
+        loss = ((out['rgb_map'] - target) ** 2).mean()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    # kernel shares
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+    rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:12]
+    tot = sum(r.device_time_total for r in prof.key_averages()) or 1.0
+    line = {"metric": "train step, %d rays (march_rays_train + field + composite + backward + Adam)" % args.rays, "ms_per_step": ms,
+            "rays_per_s": args.rays / (ms / 1000.0), "loss": float(loss), "grads_finite": bool(all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)),
+            "top_kernels": [{"name": r.key[:70], "share": r.device_time_total / tot, "calls": r.count} for r in rows]}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -559,3 +559,29 @@ def test_fused_single_kernel_mode_still_matches_oracle():
     r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "smoke ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_sequence_renderer_pipelined_frames_equal_single_frame_calls():
+    """sequence.SequenceRenderer (pinned-host condition windows in, pinned-host RGB8 ring out, frames pipelined over a copy stream)
+    must return exactly the frames that individual render_fused calls produce."""
+    import numpy as np
+    from geneface_b200 import sequence, synthetic
+    from geneface_b200.utils import convert_poses, orbit_pose
+    H = W = 32
+    model, hp = synthetic.build_model(torso=True, bitfield='S', seed=5)
+    fi = synthetic.frame_inputs(H, W)
+    F = 5
+    poses = torch.stack([torch.from_numpy(orbit_pose(3.35, 4.0 * f)) for f in range(F)])
+    g = torch.Generator().manual_seed(7)
+    conds = torch.randn(F, 5, 1, 204, generator=g).pin_memory()
+    seq = sequence.SequenceRenderer(model, H, W, fi['intrinsics'], precision='fp16', max_steps=hp['max_steps'], dt_gamma=hp['dt_gamma'], torso=True)
+    host = seq.render(poses, conds, fi['bg_color'], 1, F)
+    assert host.shape == (F - 1, H, W, 3) and host.dtype == torch.uint8
+    with torch.no_grad():
+        for k, f in enumerate(range(1, F)):
+            cf = model.cal_cond_feat(conds[f].cuda())
+            out = model.render_fused(cf, H, W, pose=poses[f], intrinsics=fi['intrinsics'], bg_color=fi['bg_color'],
+                                     torso_pose=convert_poses(poses[f:f + 1]), dt_gamma=hp['dt_gamma'], max_steps=hp['max_steps'],
+                                     precision='fp16', want=('rgb8',))
+            assert np.array_equal(out['rgb8'].cpu().numpy().reshape(H, W, 3), host[k].numpy()), f"frame {f} differs"
