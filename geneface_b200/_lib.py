@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
                 os.path.getmtime(os.path.join(_INCLUDE, "gfrender.h")),
                 *[os.path.getmtime(os.path.join(_CSRC, h)) for h in os.listdir(_CSRC) if h.endswith(".cuh")]):
             continue
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", _INCLUDE, "-c", path, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("GF_NVCC_EXTRA", "").split() + ["-I", _INCLUDE, "-c", path, "-o", obj]   # GF_NVCC_EXTRA: experiment switches (-D...)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

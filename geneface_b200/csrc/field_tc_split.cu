@@ -102,6 +102,24 @@ __global__ void k_tc_pack_split(TcPackSrc2 s, uint8_t* __restrict__ imgA, uint8_
     if (n < 16) put_half2(imgB, WB2_COL1, 16, n, k, n < 3 ? s.c1[(size_t)n * 128 + k] : 0.f, false);
 }
 
+// MMA completion for a consumer stream: only the stream's first warp polls the mbarrier; the other three park on a hardware
+// named barrier (a parked warp takes no issue slots, a polling warp does: the try_wait loops were 11 % of all issued instructions).
+// (experimental, -DGF_PARK_WARPS=1; the default lets every consumer thread poll the mbarrier itself)
+#ifndef GF_PARK_WARPS
+#define GF_PARK_WARPS 0
+#endif
+__device__ __forceinline__ void stream_wait_mma(uint32_t bar_mma, uint32_t& phase, bool polling_warp, uint32_t bar_id) {
+#if GF_PARK_WARPS
+    if (polling_warp) mbar_wait(bar_mma, phase);
+    phase ^= 1;
+    bar_named(bar_id, 128);
+#else
+    (void)polling_warp; (void)bar_id;
+    mbar_wait(bar_mma, phase);
+    phase ^= 1;
+#endif
+}
+
 struct SpArgs {
     GridDesc grid;              // A: 3-D position grid; B: 2-D ambient grid
     float bound, inv2b;
@@ -334,7 +352,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
                 for (int k = 0; k < 2; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WA_A0 + 64 + 32 * k), idesc_f16(128), 1);
                 mma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, phase); phase ^= 1;
+            stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
             tc_fence_after();
             if (leader) mbar_arrive(bar_empty + 8 * slot);                // the feature tile has been consumed
             epilogue_relu_to_A_n<true, 4>(t_d, t_d + SP_TM_AHI, t_d + SP_TM_ALO, 0, bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);
@@ -353,7 +371,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
                     mma_ts(m_d, m_d + SP_TM_AHI + 8 * k, smem_desc(w_addr + WA_A1L + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), 1);
                 mma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, phase); phase ^= 1;
+            stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
             tc_fence_after();
             // ambient output layer (128 -> 2) in fp32 from the accumulator, weights from the constant bank; tanh
             float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;          // (even, odd) column partial sums of the two outputs
@@ -474,7 +492,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                 for (int k = 0; k < 4; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WB2_SIG0 + 32 * k), idesc_f16(128), k);
                 mma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, phase); phase ^= 1;
+            stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
             tc_fence_after();
             epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 3 * 128 * 144 : nullptr);
             tc_fence_before();
@@ -499,7 +517,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                 *reinterpret_cast<uint4*>(F + sw128(row, 5)) = make_uint4(p[4], p[5], p[6], p[7]);
                 fence_async_smem();
             }
-            mbar_wait(bar_mma, phase); phase ^= 1;
+            stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
             tc_fence_after();
             epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 4 * 128 * 144 : nullptr);
             tc_fence_before();
@@ -513,7 +531,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                 mma_ss(m_d, smem_desc(f_addr + 64), smem_desc(w_addr + WB2_SH), idesc_f16(128), 1);
                 mma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, phase); phase ^= 1;
+            stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
             tc_fence_after();
             if (leader) mbar_arrive(bar_empty + 8 * slot);                // last reader of the feature tile is done
             float sg[4];
@@ -531,7 +549,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                     mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_COL1 + (k >> 2) * (16 * 128) + 32 * (k & 3)), idesc_f16(16), k);
                 mma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, phase); phase ^= 1;
+            stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
             tc_fence_after();
             float c[4];
             tmem_ld4(t_d, c);
