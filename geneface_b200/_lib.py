@@ -15,7 +15,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 _SO = os.path.join(_PKG, "libgfrender.so")
 _INCLUDE = os.path.join(os.path.dirname(_PKG), "include")
 
-SOURCES = ["api.cu", "raymarch_ops.cu", "encoders.cu", "render_fused.cu", "field_tc.cu", "field_tc_split.cu"]
+SOURCES = ["api.cu", "raymarch_ops.cu", "encoders.cu", "render_fused.cu", "field_tc.cu", "field_tc_split.cu", "adnerf_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -103,6 +103,11 @@ _SIGS = {
     "gf_sh_encode_backward": [c_vp, c_vp, c_u32, c_u32, c_u32, c_vp, c_vp, c_vp],
     "gf_freq_encode_forward": [c_vp, c_u32, c_u32, c_u32, c_u32, c_vp, c_vp],
     "gf_freq_encode_backward": [c_vp, c_vp, c_u32, c_u32, c_u32, c_u32, c_vp, c_vp],
+    "gf_adnerf_get_rays": [c_u32, c_u32, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "gf_adnerf_embed": [c_vp, c_u32, c_u32, c_u32, c_vp, c_u32, c_vp],
+    "gf_adnerf_embed_points": [c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_vp, c_u32, c_vp],
+    "gf_adnerf_raw2outputs": [c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "gf_adnerf_sample_pdf": [c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_int, c_vp, c_vp, c_vp],
     "gf_model_create": [c_vp, c_vp, c_vp],
     "gf_model_destroy": [c_vp],
     "gf_model_packed_bytes": [c_vp],

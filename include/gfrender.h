@@ -130,6 +130,34 @@ GF_API int gf_freq_encode_backward(const float* grad, const float* outputs, uint
                                    uint32_t C, float* grad_inputs, gf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Vanilla AD-NeRF path (modules/nerfs): the non-GEMM operators.
+ * Inference only.  All tensors fp32, contiguous; the caller allocates every output.
+ *   gf_adnerf_get_rays       modules/nerfs/commons/ray_samplers.py:11-44 (get_rays) + the viewdirs normalisation of
+ *                            volume_rendering.py:251-259; c2w is 3x4 row-major; viewdirs may be NULL
+ *   gf_adnerf_embed          modules/nerfs/commons/embedders.py:5-45 (FreqEmbedder.forward), x [n, D] -> out rows of
+ *                            D*(1+2*multi_res) floats at stride ld (floats)
+ *   gf_adnerf_embed_points   volume_rendering.py:153,183 (pts = o + d z) fused with the position embedding
+ *   gf_adnerf_raw2outputs    volume_rendering.py:9-59 (raw [R,S,4] = rgb logits + sigma, raw_noise_std = 0); any output but
+ *                            rgb_map may be NULL
+ *   gf_adnerf_sample_pdf     volume_rendering.py:62-96 on (z_mid, weights[1:-1]) as called from :177-182, followed by the
+ *                            concatenate + sort; u NULL = det (perturb == 0), else [R, N_importance] uniform numbers;
+ *                            merge = 1: z_vals / weights are the coarse depths and their weights [R,S], z_out [R, S+N_importance]
+ *                            is the sorted union; merge = 0: plain sample_pdf(bins [R,S], weights [R,S-1]) -> z_out [R, N_importance];
+ *                            samples_out (optional) the N new depths (for z_std)
+ * ---------------------------------------------------------------------------------- */
+GF_API int gf_adnerf_get_rays(uint32_t H, uint32_t W, float focal, float cx, float cy, const float* c2w, float* rays_o,
+                              float* rays_d, float* viewdirs, gf_stream_t stream);
+GF_API int gf_adnerf_embed(const float* x, uint32_t n, uint32_t D, uint32_t multi_res, float* out, uint32_t ld,
+                           gf_stream_t stream);
+GF_API int gf_adnerf_embed_points(const float* rays_o, const float* rays_d, const float* z_vals, uint32_t R, uint32_t S,
+                                  uint32_t multi_res, float* out, uint32_t ld, gf_stream_t stream);
+GF_API int gf_adnerf_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, const float* bc_rgb, uint32_t R,
+                                 uint32_t S, int white_bkgd, float* rgb_map, float* disp_map, float* acc_map, float* weights,
+                                 float* depth_map, float* rgb_map_fg, gf_stream_t stream);
+GF_API int gf_adnerf_sample_pdf(const float* z_vals, const float* weights, const float* u, uint32_t R, uint32_t S,
+                                uint32_t N_importance, int merge, float* z_out, float* samples_out, gf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Fused frame renderer: replaces the eval branch of NeRFRenderer.render()
  * (modules/radnerfs/renderer.py:263-367) and RADNeRFTorso.render()
  * (modules/radnerfs/radnerf_torso.py:86-198) -- ray generation, aabb test, occupancy

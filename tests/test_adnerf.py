@@ -1,0 +1,140 @@
+"""Vanilla AD-NeRF path: geneface_b200.adnerf against the oracle port (oracle/adnerf_port.py) and the
+golden frame produced by the real reference (tests/golden/adnerf.npz, oracle/gen_golden_adnerf.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import adnerf_port
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _model(device):
+    from geneface_b200 import adnerf
+    m = adnerf.ADNeRF(dict(cond_dim=64, hidden_size=256))
+    sd = adnerf_port.init_state(seed=0)
+    m.load_state_dict(sd, strict=True)            # the reference's own key names
+    return m.to(device).eval(), sd
+
+
+def test_state_dict_keys_and_folded_backbone_equals_reference_form_cpu():
+    """No GPU needed: the folded evaluation (cond / view embedding as biases) is the same function as backbone.py's concatenating form."""
+    m, sd = _model("cpu")
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    g = torch.Generator().manual_seed(0)
+    R, S = 5, 7
+    pe = torch.randn(R * S, 63, generator=g)
+    cond = torch.randn(64, generator=g)
+    ve = torch.randn(R, 27, generator=g)
+    with torch.no_grad():
+        for net in (m.model_coarse, m.model_fine):
+            a = net(pe.view(R, S, 63), cond, ve)
+            b = net.forward_folded(pe, cond, ve, S).view(R, S, 4)
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+        # and equals the oracle port's backbone
+        o = adnerf_port.backbone(sd, "model_fine", pe.view(R, S, 63), cond, ve)
+        assert torch.allclose(o, m.model_fine(pe.view(R, S, 63), cond, ve), rtol=1e-4, atol=1e-5)
+        cond_in = torch.randn(8, 16, 29, generator=g)
+        assert torch.allclose(m.cal_cond_feat(cond_in, with_att=True), adnerf_port.cal_cond_feat(sd, cond_in, True), rtol=1e-5, atol=1e-6)
+
+
+def test_cpu_tensors_are_refused():
+    from geneface_b200 import adnerf
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        adnerf.raw2outputs(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.zeros(2, 3), torch.zeros(2, 3))
+
+
+@pytest.mark.gpu
+def test_rays_and_embedding_vs_oracle():
+    from geneface_b200 import adnerf
+    H, W = 12, 20
+    focal = 1200.0 * H / 450.0
+    c2w = torch.tensor([[0.8, 0.0, 0.6, 0.1], [0.0, 1.0, 0.0, -0.2], [-0.6, 0.0, 0.8, 0.6]])
+    ro, rd = adnerf.get_rays(H, W, focal, c2w.cuda(), W / 2, H / 2)
+    ro_o, rd_o = adnerf_port.get_rays(H, W, focal, c2w, W / 2, H / 2)
+    assert torch.allclose(ro.cpu(), ro_o.expand_as(rd_o), atol=1e-7) and torch.allclose(rd.cpu(), rd_o, rtol=1e-6, atol=1e-7)
+    x = torch.randn(1000, 3, generator=torch.Generator().manual_seed(1))
+    for L in (10, 4):
+        e = adnerf.FreqEmbedder(3, L)(x.cuda()).cpu()
+        assert e.shape == (1000, 3 * (1 + 2 * L))
+        assert torch.allclose(e, adnerf_port.freq_embed(x, L), rtol=1e-5, atol=2e-5)     # |x 2^9| ~ 1e3: sin/cos argument rounding
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S", [64, 192, 33])
+def test_raw2outputs_vs_oracle(S):
+    from geneface_b200 import adnerf
+    g = torch.Generator().manual_seed(S)
+    R = 257
+    raw = torch.randn(R, S, 4, generator=g) * 3
+    z, _ = torch.sort(torch.rand(R, S, generator=g) * 0.6 + 0.3, -1)
+    rd = torch.randn(R, 3, generator=g)
+    bc = torch.rand(R, 3, generator=g)
+    rgb_o, acc_o, w_o, depth_o = adnerf_port.raw2outputs(raw, z, rd, bc)
+    rgb, disp, acc, w, depth, rgb_fg = adnerf.raw2outputs(raw.cuda(), z.cuda(), rd.cuda(), bc.cuda())
+    assert torch.allclose(w.cpu(), w_o, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(rgb.cpu(), rgb_o, rtol=1e-4, atol=1e-5) and torch.allclose(acc.cpu(), acc_o, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(depth.cpu(), depth_o, rtol=1e-4, atol=1e-5)
+    fg_o = torch.sum(w_o[:, :-1, None] * torch.sigmoid(raw[:, :-1, :3]), -2)
+    assert torch.allclose(rgb_fg.cpu(), fg_o, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(disp.cpu(), 1.0 / torch.clamp(depth_o / acc_o, min=1e-10), rtol=1e-3)
+
+
+@pytest.mark.gpu
+def test_sample_pdf_plain_and_merged_vs_oracle():
+    from geneface_b200 import adnerf
+    g = torch.Generator().manual_seed(3)
+    R, S, N = 300, 64, 128
+    z, _ = torch.sort(torch.rand(R, S, generator=g) * 0.6 + 0.3, -1)
+    w = torch.rand(R, S, generator=g) ** 4
+    w[::7] = 0.0                                          # flat pdf rows (the 1e-5 floor decides)
+    mids = 0.5 * (z[:, 1:] + z[:, :-1])
+    ref = adnerf_port.sample_pdf_det(mids, w[:, 1:-1], N)
+    got = adnerf.sample_pdf(mids.cuda(), w[:, 1:-1].cuda(), N, det=True).cpu()
+    # the inverse CDF is continuous, so a cdf entry rounded the other way moves a sample by O(eps) only -- except at u = 1 exactly
+    # (last column): there the reference's own result jumps between the last two bins according to whether the float cumsum ends
+    # just below or just above 1 when the last pdf bin is under the 1e-5 denominator guard.
+    assert torch.allclose(got[:, :-1], ref[:, :-1], rtol=0, atol=2e-5)
+    assert bool(((got[:, -1] >= mids[:, -2] - 1e-6) & (got[:, -1] <= mids[:, -1] + 1e-6)).all())
+    zz, zs = adnerf._importance_depths(z.cuda(), w.cuda(), N, det=True)
+    assert zz.shape == (R, S + N) and bool((zz[:, 1:] >= zz[:, :-1]).all())
+    assert torch.allclose(zs.cpu(), got, rtol=0, atol=1e-7)                       # same sampler in both modes
+    merged_ref, _ = torch.sort(torch.cat([z, got], -1), -1)
+    assert torch.allclose(zz.cpu(), merged_ref, rtol=0, atol=1e-7)
+    rnd = adnerf.sample_pdf(mids.cuda(), w[:, 1:-1].cuda(), 50, det=False).cpu()
+    assert rnd.shape == (R, 50) and bool(((rnd >= mids[:, :1] - 1e-6) & (rnd <= mids[:, -1:] + 1e-6)).all())
+
+
+@pytest.mark.gpu
+def test_frame_matches_the_real_reference_golden_and_the_port():
+    from geneface_b200 import adnerf
+    m, sd = _model("cuda")
+    gold = np.load(os.path.join(GOLDEN, "adnerf.npz"))
+
+    def render(H, W, chunk):
+        focal = 1200.0 * H / 450.0
+        c2w = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 1.0, 0.6]]).cuda()
+        cond = torch.randn(8, 16, 29, generator=torch.Generator().manual_seed(1)).cuda()
+        with torch.no_grad():
+            cf = m.cal_cond_feat(cond, with_att=True)
+            out = adnerf.render_dynamic_face(H, W, focal, W / 2, H / 2, chunk=chunk, c2w=c2w, cond=cf, near=0.3, far=0.9, network_fn=m,
+                                             N_samples=64, N_importance=128, perturb=0., bc_rgb=torch.ones(H, W, 3).cuda())
+        return cf, out
+
+    cf, (rgb, disp, acc, last_w, rgb_fg, extras) = render(16, 16, 100)          # ragged chunks on purpose
+    assert np.allclose(cf.cpu().numpy(), gold["cond_feat"], atol=1e-5)
+    for name, got, ref in (("rgb", rgb, gold["rgb"]), ("acc", acc, gold["acc"]), ("last_weight", last_w, gold["last_weight"])):
+        err = np.abs(got.cpu().numpy() - ref) / (1e-5 + np.abs(ref))
+        print(f"adnerf {name}: worst rel err vs the real reference {err.max():.2e}")
+        assert err.max() < 1e-3, name
+    assert set(extras) >= {"rgb_map_coarse", "disp_map_coarse", "accu_map_coarse", "z_std", "last_weight0", "rgb_map_fg0"}
+    # a second size against the CPU port, generic (non-folded) network path through forward()
+    H = W = 24
+    _, (rgb2, _, acc2, lw2, _, _) = render(H, W, 4096)
+    rgb_o, acc_o, lw_o = adnerf_port.render_frame(sd, H, W)
+    assert np.abs(rgb2.cpu().numpy() - rgb_o.numpy()).max() < 1e-3 and np.abs(acc2.cpu().numpy() - acc_o.numpy()).max() < 1e-3
+    with pytest.raises(KeyError):
+        adnerf.render_dynamic_face(8, 8, 20.0, 4, 4, c2w=torch.eye(4).cuda()[:3], cond=cf, network_fn=m, N_samples=8, N_importance=0,
+                                   bc_rgb=torch.ones(8, 8, 3).cuda())
