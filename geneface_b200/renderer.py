@@ -128,72 +128,68 @@ class NeRFRenderer(nn.Module):
         self.local_step = 0
 
     # -- density grid maintenance (renderer.py:128-260), on our morton3D / dilation / packbits ops -----------
+    # The reference walks the H^3 grid in S^3 blocks with three nested Python loops; a B200 holds the whole grid's coordinate
+    # list (H^3 x 3 int32 = 25 MB at H=128) and evaluates a cascade in one field call, so both routines work on the full
+    # cell list at once: `_cells()` returns (integer coords [H^3,3], morton index [H^3], centre in [-1,1]^3).
+    def _cells(self):
+        G, dev = self.grid_size, self.density_bitfield.device
+        ar = torch.arange(G, dtype=torch.int32, device=dev)
+        coords = torch.stack(torch.meshgrid(ar, ar, ar, indexing='ij'), dim=-1).view(-1, 3).contiguous()
+        return coords, raymarching.morton3D(coords).long(), coords.float() * (2.0 / (G - 1)) - 1.0
+
+    def _cascade_extent(self, cas):
+        bound = min(2 ** cas, self.bound)
+        return bound, bound / self.grid_size                 # (half extent of the cascade, half a cell)
+
     @torch.no_grad()
     def mark_untrained_grid(self, poses, intrinsic, S=64):
+        """Cells no training camera ever sees get density -1 (never sampled, never updated).  S = camera batch."""
         if not self.cuda_ray:
             return
         if isinstance(poses, np.ndarray):
             poses = torch.from_numpy(poses)
         fx, fy, cx, cy = intrinsic
-        dev = self.density_bitfield.device
-        poses = poses.to(dev)
-        B = poses.shape[0]
-        count = torch.zeros_like(self.density_grid)
-        axis = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
-        for xs in axis:
-            for ys in axis:
-                for zs in axis:
-                    xx, yy, zz = custom_meshgrid(xs, ys, zs)
-                    coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
-                    indices = raymarching.morton3D(coords).long()
-                    world = (2 * coords.float() / (self.grid_size - 1) - 1).unsqueeze(0)
-                    for cas in range(self.cascade):
-                        bound = min(2 ** cas, self.bound)
-                        hgs = bound / self.grid_size
-                        cas_world = world * (bound - hgs)
-                        for head in range(0, B, S):
-                            tail = min(head + S, B)
-                            cam = cas_world - poses[head:tail, :3, 3].unsqueeze(1)
-                            cam = cam @ poses[head:tail, :3, :3]
-                            mask = (cam[:, :, 2] > 0) & (cam[:, :, 0].abs() < cx / fx * cam[:, :, 2] + hgs * 2) & \
-                                   (cam[:, :, 1].abs() < cy / fy * cam[:, :, 2] + hgs * 2)
-                            count[cas, indices] += mask.sum(0).reshape(-1)
-        self.density_grid[count == 0] = -1
+        poses = poses.to(self.density_bitfield.device).float()
+        _, morton, centre = self._cells()
+        seen = torch.zeros_like(self.density_grid)
+        for cas in range(self.cascade):
+            bound, half_cell = self._cascade_extent(cas)
+            world = centre * (bound - half_cell)                                        # [H^3, 3]
+            hits = torch.zeros(world.shape[0], device=world.device)
+            for k in range(0, poses.shape[0], S):
+                R, t = poses[k:k + S, :3, :3], poses[k:k + S, :3, 3]
+                cam = (world[None] - t[:, None]) @ R                                    # [b, H^3, 3] camera frame (z forward)
+                z = cam[..., 2]
+                inside = (z > 0) & (cam[..., 0].abs() < cx / fx * z + 2 * half_cell) & (cam[..., 1].abs() < cy / fy * z + 2 * half_cell)
+                hits += inside.sum(0)
+            seen[cas, morton] = hits
+        self.density_grid[seen == 0] = -1
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128):
+        """EMA-max update of the occupancy grid from the current field at one jittered point per cell, dilation, bitfield repack."""
         if not self.cuda_ray:
             return
         dev = self.density_bitfield.device
         rand_idx = random.randint(0, self.conds.shape[0] - 1)
-        cond = get_audio_features(self.conds, 2, rand_idx, self.smo_win_size).to(dev)
-        enc_a = self.cal_cond_feat(cond)
-        tmp_grid = torch.zeros_like(self.density_grid)
-        axis = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
-        for xs in axis:
-            for ys in axis:
-                for zs in axis:
-                    xx, yy, zz = custom_meshgrid(xs, ys, zs)
-                    coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
-                    indices = raymarching.morton3D(coords).long()
-                    xyzs = 2 * coords.float() / (self.grid_size - 1) - 1
-                    for cas in range(self.cascade):
-                        bound = min(2 ** cas, self.bound)
-                        hgs = bound / self.grid_size
-                        cas_xyzs = xyzs * (bound - hgs)
-                        cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * hgs
-                        sigmas = self.density(cas_xyzs, enc_a)['sigma'].reshape(-1).detach().to(tmp_grid.dtype)
-                        tmp_grid[cas, indices] = sigmas * self.density_scale
-        tmp_grid = raymarching.morton3D_dilation(tmp_grid)
-        valid = (self.density_grid >= 0) & (tmp_grid >= 0)
-        self.density_grid[valid] = torch.maximum(self.density_grid[valid] * decay, tmp_grid[valid])
+        enc_a = self.cal_cond_feat(get_audio_features(self.conds, 2, rand_idx, self.smo_win_size).to(dev))
+        _, morton, centre = self._cells()
+        fresh = torch.zeros_like(self.density_grid)
+        for cas in range(self.cascade):
+            bound, half_cell = self._cascade_extent(cas)
+            pts = centre * (bound - half_cell)
+            pts = pts + (torch.rand_like(pts) * 2 - 1) * half_cell
+            sigma = self.density(pts, enc_a)['sigma'].reshape(-1).detach()
+            fresh[cas, morton] = sigma.to(fresh.dtype) * self.density_scale
+        fresh = raymarching.morton3D_dilation(fresh)
+        live = (self.density_grid >= 0) & (fresh >= 0)
+        self.density_grid[live] = torch.maximum(self.density_grid[live] * decay, fresh[live])
         self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
         self.iter_density += 1
-        density_thresh = min(self.mean_density, self.density_thresh)
-        self.density_bitfield = raymarching.packbits(self.density_grid, density_thresh, self.density_bitfield)
-        total_step = min(16, self.local_step)
-        if total_step > 0:
-            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        self.density_bitfield = raymarching.packbits(self.density_grid, min(self.mean_density, self.density_thresh), self.density_bitfield)
+        steps = min(16, self.local_step)
+        if steps > 0:
+            self.mean_count = int(self.step_counter[:steps, 0].sum().item() / steps)
         self.local_step = 0
         self._gf_key = None   # bitfield changed -> rebuild fused model lazily
 
@@ -645,24 +641,21 @@ class RADNeRFTorso(RADNeRF):
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128):
-        """radnerf_torso.py:200-241 (torso 2D occupancy grid only)."""
-        dev = self.density_bitfield.device
-        tmp = torch.zeros_like(self.density_grid_torso)
+        """radnerf_torso.py:200-241 (torso 2D occupancy grid only): alpha of the torso field at one jittered point per cell of the
+        H x H image-plane grid, 5x5 max-dilation, EMA-max.  The whole grid (16 K cells) is one field call."""
+        G, dev = self.grid_size, self.density_bitfield.device
         rand_idx = random.randint(0, self.poses.shape[0] - 1)
         pose = convert_poses(self.poses[[rand_idx]]).to(dev)
         code = self.torso_individual_codes[[rand_idx]] if self.torso_individual_embedding_dim > 0 else None
-        axis = torch.arange(self.grid_size, dtype=torch.int32, device=dev).split(S)
-        hgs = 1 / self.grid_size
-        for xs in axis:
-            for ys in axis:
-                xx, yy = custom_meshgrid(xs, ys)
-                coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1)], dim=-1)
-                indices = (coords[:, 1] * self.grid_size + coords[:, 0]).long()      # x/y transposed, as the reference
-                xys = (2 * coords.float() / (self.grid_size - 1) - 1) * (1 - hgs)
-                xys += (torch.rand_like(xys) * 2 - 1) * hgs
-                alphas, _, _ = self.forward_torso(xys, pose, code)
-                tmp[indices] = alphas.squeeze(1).float()
-        tmp = F.max_pool2d(tmp.view(1, 1, self.grid_size, self.grid_size), kernel_size=5, stride=1, padding=2).view(-1)
-        self.density_grid_torso = torch.maximum(self.density_grid_torso * decay, tmp)
+        ar = torch.arange(G, dtype=torch.int32, device=dev)
+        cell = torch.stack(torch.meshgrid(ar, ar, indexing='ij'), dim=-1).view(-1, 2)
+        half_cell = 1 / G
+        xys = (cell.float() * (2.0 / (G - 1)) - 1.0) * (1 - half_cell)
+        xys = xys + (torch.rand_like(xys) * 2 - 1) * half_cell
+        alphas, _, _ = self.forward_torso(xys, pose, code)
+        fresh = torch.zeros_like(self.density_grid_torso)
+        fresh[(cell[:, 1] * G + cell[:, 0]).long()] = alphas.squeeze(1).float()          # x/y transposed, as the reference stores it
+        fresh = F.max_pool2d(fresh.view(1, 1, G, G), kernel_size=5, stride=1, padding=2).view(-1)
+        self.density_grid_torso = torch.maximum(self.density_grid_torso * decay, fresh)
         self.mean_density_torso = torch.mean(self.density_grid_torso).item()
         self._gf_key = None

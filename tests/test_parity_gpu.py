@@ -585,3 +585,62 @@ def test_sequence_renderer_pipelined_frames_equal_single_frame_calls():
                                      torso_pose=convert_poses(poses[f:f + 1]), dt_gamma=hp['dt_gamma'], max_steps=hp['max_steps'],
                                      precision='fp16', want=('rgb8',))
             assert np.array_equal(out['rgb8'].cpu().numpy().reshape(H, W, 3), host[k].numpy()), f"frame {f} differs"
+
+
+@pytest.mark.gpu
+def test_density_grid_maintenance_vs_oracle(monkeypatch):
+    """update_extra_state / mark_untrained_grid on a 32^3 x 2-cascade grid with the per-cell jitter
+    switched off (torch.rand_like -> 0.5), against a CPU restatement: field density at the cell centres (FieldOracle), morton
+    scatter, dilation, EMA-max, mean, packbits (oracle/cpu_ops)."""
+    import numpy as np
+    from geneface_b200 import synthetic
+    from oracle import cpu_ops, field as OF
+    G, C = 32, 2
+    model, hp = synthetic.build_model(torso=False, bitfield='F', seed=3, grid_size=G, bound=2)
+    assert model.cascade == C
+    model.conds = torch.randn(12, 1, 204, generator=torch.Generator().manual_seed(5))
+    # --- mark_untrained_grid: one camera looking down -z from z = +3 -> cells behind it or outside the frustum are -1
+    pose = torch.eye(4)[None].clone()
+    pose[0, 2, 3] = -3.0
+    model.density_grid.zero_()
+    model.mark_untrained_grid(pose, (60.0, 60.0, 32.0, 32.0))
+    dg = model.density_grid.cpu().numpy()
+    ar = np.arange(G, dtype=np.int32)
+    coords = np.stack(np.meshgrid(ar, ar, ar, indexing='ij'), -1).reshape(-1, 3)
+    morton = cpu_ops.morton3D(coords).astype(np.int64)
+    centre = coords.astype(np.float32) * (2.0 / (G - 1)) - 1.0
+    for cas in range(C):
+        bound = min(2 ** cas, 2)
+        hc = bound / G
+        w = centre * (bound - hc)
+        z = w[:, 2] + 3.0
+        seen = (z > 0) & (np.abs(w[:, 0]) < 32.0 / 60.0 * z + 2 * hc) & (np.abs(w[:, 1]) < 32.0 / 60.0 * z + 2 * hc)
+        exp = np.zeros(G ** 3, np.float32)
+        exp[morton] = np.where(seen, 0.0, -1.0)
+        assert np.array_equal(dg[cas], exp), f"untrained mask differs in cascade {cas}"
+    # --- update_extra_state without jitter
+    model.density_grid.zero_()
+    monkeypatch.setattr(torch, "rand_like", lambda t, **k: torch.full_like(t, 0.5))
+    import random
+    random.seed(11)
+    model.update_extra_state()
+    random.seed(11)
+    idx = random.randint(0, model.conds.shape[0] - 1)
+    from geneface_b200.utils import get_audio_features
+    sd = synthetic.state_to_numpy(model)
+    cf = OF.cal_cond_feat(sd, get_audio_features(model.conds, 2, idx, model.smo_win_size).numpy())
+    fo = OF.FieldOracle(sd, bound=2.0)
+    fresh = np.zeros((C, G ** 3), np.float32)
+    for cas in range(C):
+        bound = min(2 ** cas, 2)
+        pts = (centre * (bound - bound / G)).astype(np.float32)
+        sigma, _, _ = fo.forward(pts, np.tile(np.array([[0, 0, 1]], np.float32), (pts.shape[0], 1)), cf, sd['individual_embeddings'][0])
+        fresh[cas, morton] = sigma
+    fresh = cpu_ops.morton3D_dilation(fresh)
+    exp_grid = np.maximum(0.0 * 0.95, fresh)                       # grid was zero: EMA-max leaves the dilated field
+    got = model.density_grid.cpu().numpy()
+    assert np.allclose(got, exp_grid, rtol=2e-3, atol=1e-5), float(np.abs(got - exp_grid).max())
+    mean = float(np.clip(got, 0, None).mean())
+    assert abs(model.mean_density - mean) < 1e-6 * max(1.0, mean)
+    thresh = min(mean, model.density_thresh)
+    assert np.array_equal(model.density_bitfield.cpu().numpy(), cpu_ops.packbits(got, thresh))
