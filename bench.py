@@ -364,9 +364,46 @@ def main():
             line["may_cfg"] = may_cfg_fps(dev, args.precision, not args.no_ref_cuda)
         except Exception as e:  # noqa: BLE001
             line["may_cfg"] = {"unavailable": repr(e)[:200]}
+        try:
+            line["adnerf_gpu"] = adnerf_gpu_fps(dev)
+        except Exception as e:  # noqa: BLE001
+            line["adnerf_gpu"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def adnerf_gpu_fps(dev):
+    """Context number (BASELINE.json configs[0] on the GPU): the vanilla AD-NeRF frame -- 64x64 rays, 64 coarse + 128 fine samples,
+    8x256 backbone -- through geneface_b200.adnerf (C-ABI operators + library GEMMs); `adnerf_cpu` in the reference arm is its CPU twin."""
+    import torch
+    from geneface_b200 import adnerf
+    torch.manual_seed(0)
+    m = adnerf.ADNeRF(dict(cond_dim=64, hidden_size=256)).to(dev).eval()
+    Hh = Ww = 64
+    focal = 1200.0 * Hh / 450.0
+    c2w = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 1.0, 0.6]], device=dev)
+    cond = torch.randn(8, 16, 29, generator=torch.Generator().manual_seed(1)).to(dev)
+    bc = torch.ones(Hh, Ww, 3, device=dev)
+
+    def frame():
+        with torch.no_grad():
+            cf = m.cal_cond_feat(cond, with_att=True)
+            return adnerf.render_dynamic_face(Hh, Ww, focal, Ww / 2, Hh / 2, chunk=4096, c2w=c2w, cond=cf, near=0.3, far=0.9, network_fn=m,
+                                              N_samples=64, N_importance=128, perturb=0., bc_rgb=bc)
+    for _ in range(3):
+        frame()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    e0.record()
+    for _ in range(n):
+        out = frame()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"value": 1000.0 / ms, "unit": "frames/s", "ms_per_frame": ms, "finite": bool(torch.isfinite(out[0]).all()),
+            "workload": "vanilla AD-NeRF 64x64, 64 coarse + 128 fine samples/ray, fp32 GEMMs, random weights (BASELINE.json configs[0])"}
 
 
 def may_cfg_fps(dev, precision, with_ref):
