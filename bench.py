@@ -246,7 +246,6 @@ def main():
     handle = model.gf_model()
     L = _lib.lib()
     rgb8 = torch.empty(N, 3, dtype=torch.uint8, device=dev)
-    host_rgb8 = torch.empty(N, 3, dtype=torch.uint8).pin_memory()
     counters = torch.zeros(4, dtype=torch.int64, device=dev)
     outbuf = {'rgb8': rgb8, 'counters': counters}
 
