@@ -49,7 +49,7 @@ class SequenceRenderer:
         self.precision, self.max_steps, self.dt_gamma, self.torso = precision, max_steps, dt_gamma, torso
 
     @torch.no_grad()
-    def render(self, poses, conds, bg_color, start, end, out_rgb8=None):
+    def render(self, poses, conds, bg_color, start, end, out_rgb8=None, sink=None):
         """poses [F,4,4] (host or device), conds [F,smo,win,C] (device, or PINNED HOST: each frame's window is then copied host->device
         asynchronously inside the loop), bg_color [1,N,3]; returns uint8 [end-start, H, W, 3] pinned host tensor.  Frames are pipelined:
         frame k+1 is enqueued while frame k's RGB8 drains to the host ring on a copy stream; one synchronisation at the end."""
@@ -60,6 +60,15 @@ class SequenceRenderer:
         dev_rgb8 = [torch.empty(N, 3, dtype=torch.uint8, device='cuda') for _ in range(2)]
         copy_stream = torch.cuda.Stream()
         done = [None, None]
+        landed, flushed = [], 0                    # per-frame "in host memory" events; frames already handed to the sink
+
+        def flush(upto):
+            nonlocal flushed
+            while sink is not None and flushed < upto:
+                landed[flushed].synchronize()
+                sink(start + flushed, host[flushed].numpy())
+                flushed += 1
+
         for k, f in enumerate(range(start, end)):
             slot = k & 1
             if done[slot] is not None:
@@ -79,6 +88,9 @@ class SequenceRenderer:
                 host[k].view(-1, 3).copy_(dev_rgb8[slot], non_blocking=True)
                 done[slot] = torch.cuda.Event()
                 done[slot].record(copy_stream)
+                landed.append(done[slot])
+            flush(k - 1)
         copy_stream.synchronize()
         torch.cuda.current_stream().synchronize()
+        flush(n)
         return host

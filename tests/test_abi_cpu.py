@@ -23,6 +23,8 @@ def test_header_declares_the_reference_surface():
                  "freq_encode_forward", "freq_encode_backward"):
         assert "gf_" + name in syms
     assert {"gf_model_create", "gf_model_destroy", "gf_render_frame", "gf_render_workspace_bytes", "gf_field_forward", "gf_last_error"} <= set(syms)
+    # the non-GEMM operators of the vanilla path (modules/nerfs/commons: ray_samplers, embedders, volume_rendering)
+    assert {"gf_adnerf_get_rays", "gf_adnerf_embed", "gf_adnerf_embed_points", "gf_adnerf_raw2outputs", "gf_adnerf_sample_pdf"} <= set(syms)
 
 
 def test_library_loads_and_exports_every_declared_symbol():
@@ -46,6 +48,18 @@ def test_argument_validation_happens_before_any_launch():
     assert L.gf_sh_encode_forward(one, one, 4, 3, 9, None, None) == -22
     assert b"degree in [1, 8]" in L.gf_last_error()
     assert L.gf_freq_encode_forward(one, 4, 2, 10, 41, one, None) == -22
+    # vanilla AD-NeRF operators (modules/nerfs surface)
+    assert L.gf_adnerf_embed(one, 4, 9, 10, one, 200, None) == -22
+    assert b"input dim 9" in L.gf_last_error()
+    assert L.gf_adnerf_embed(one, 4, 3, 10, one, 62, None) == -22                      # row stride below 3 * (1 + 2 * 10) = 63
+    assert b"row stride" in L.gf_last_error()
+    assert L.gf_adnerf_sample_pdf(one, one, None, 4, 2, 128, 1, one, None, None) == -22
+    assert b"at least 3" in L.gf_last_error()
+    assert L.gf_adnerf_sample_pdf(one, one, None, 4, 400, 128, 1, one, None, None) == -22
+    assert b"exceeds 512" in L.gf_last_error()
+    assert L.gf_adnerf_raw2outputs(ctypes.c_void_p(4), one, one, one, 4, 8, 0, one, None, None, None, None, None, None) == -22
+    assert b"16-byte aligned" in L.gf_last_error()
+    assert L.gf_adnerf_get_rays(0, 0, ctypes.c_float(1.0), ctypes.c_float(0.0), ctypes.c_float(0.0), one, one, one, None, None) == 0   # empty image: no launch
     with pytest.raises(RuntimeError):
         _lib.check(-22, "x")
     assert L.gf_render_workspace_bytes(512 * 512) > 512 * 512 * 32 * 40

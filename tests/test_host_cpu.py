@@ -112,3 +112,39 @@ def test_ops_fail_loudly_without_cuda():
     model, _ = synthetic.build_model(torso=False, device='cpu')
     with pytest.raises(RuntimeError):
         model.gf_model()
+
+
+def test_png_egress_roundtrip_and_parallel_writer(tmp_path):
+    """egress.encode_png writes standard PNGs (decoded here by OpenCV and by Pillow, bit-exact) and PngSequenceWriter names the
+    files like the reference's frame loop (base_nerf_infer.py:99)."""
+    import cv2
+    import numpy as np
+    from PIL import Image
+    from geneface_b200 import egress
+    rng = np.random.default_rng(0)
+    H, W = 37, 53                                                     # odd sizes: row padding / filter bookkeeping
+    yy, xx = np.mgrid[0:H, 0:W]
+    smooth = np.stack([(xx * 4) % 256, (yy * 6) % 256, (xx + yy) % 256], -1).astype(np.uint8)
+    noise = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    for img in (smooth, noise, np.zeros((1, 1, 3), np.uint8)):
+        for pred in ("none", "sub", "up"):
+            data = egress.encode_png(img, level=1, prediction=pred)
+            dec = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+            assert dec is not None and np.array_equal(dec[..., ::-1], img), pred      # OpenCV returns BGR
+            import io
+            assert np.array_equal(np.asarray(Image.open(io.BytesIO(data)).convert("RGB")), img)
+    assert len(egress.encode_png(smooth, prediction="sub")) < len(egress.encode_png(smooth, prediction="none"))
+    import pytest
+    with pytest.raises(ValueError):
+        egress.encode_png(np.zeros((4, 4), np.uint8))
+    frames = rng.integers(0, 256, (9, H, W, 3), dtype=np.uint8)
+    for backend in ("zlib", "cv2"):
+        out = tmp_path / ("frames_" + backend)
+        with egress.PngSequenceWriter(str(out), workers=4, backend=backend) as wr:
+            for k in range(9):
+                wr.submit(100 + k, frames[k])
+        names = sorted(os.listdir(out))
+        assert names == ["%05d.png" % (100 + k) for k in range(9)]
+        for k, n in enumerate(names):
+            assert np.array_equal(cv2.imread(str(out / n))[..., ::-1], frames[k])
+        assert wr.bytes_written == sum(os.path.getsize(out / n) for n in names)

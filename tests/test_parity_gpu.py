@@ -576,8 +576,10 @@ def test_sequence_renderer_pipelined_frames_equal_single_frame_calls():
     g = torch.Generator().manual_seed(7)
     conds = torch.randn(F, 5, 1, 204, generator=g).pin_memory()
     seq = sequence.SequenceRenderer(model, H, W, fi['intrinsics'], precision='fp16', max_steps=hp['max_steps'], dt_gamma=hp['dt_gamma'], torso=True)
-    host = seq.render(poses, conds, fi['bg_color'], 1, F)
+    sunk = []
+    host = seq.render(poses, conds, fi['bg_color'], 1, F, sink=lambda idx, frame: sunk.append((idx, frame.copy())))
     assert host.shape == (F - 1, H, W, 3) and host.dtype == torch.uint8
+    assert [i for i, _ in sunk] == list(range(1, F)) and all(np.array_equal(fr, host[k].numpy()) for k, (_, fr) in enumerate(sunk))
     with torch.no_grad():
         for k, f in enumerate(range(1, F)):
             cf = model.cal_cond_feat(conds[f].cuda())
