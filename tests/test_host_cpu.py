@@ -148,3 +148,44 @@ def test_png_egress_roundtrip_and_parallel_writer(tmp_path):
         for k, n in enumerate(names):
             assert np.array_equal(cv2.imread(str(out / n))[..., ::-1], frames[k])
         assert wr.bytes_written == sum(os.path.getsize(out / n) for n in names)
+
+
+def test_ingress_matches_the_reference_golden(tmp_path):
+    """ingress.py (windows, landmark regularisation, camera smoothing, dataset file) against outputs of the reference's own code
+    (oracle/gen_golden_ingress.py -> tests/golden/ingress.npz)."""
+    from geneface_b200 import ingress, utils
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ingress.npz"))
+    conds = g["win_in"]
+    for pad in ("zero", "edge"):
+        for win in (5, 8, 1):
+            ref = g[f"win_{pad}_{win}"]                                   # idx = -1 .. 11 (clamped by the reference)
+            got = np.stack([ingress.window(conds, i, win, pad) for i in range(-1, 12)])
+            assert np.array_equal(got, ref), (pad, win)
+            assert np.array_equal(ingress.windows(conds, win, pad), ref[1:12])
+    # landmarks: normalise + clamp + exponential smoothing, then the two window tensors
+    cond = ingress.regularize_lm3d(g["lm_in"], g["lm_mean"], g["lm_std"], 2.5)
+    assert cond.shape == (9, 204) and np.allclose(cond, g["lm_cond"], rtol=0, atol=1e-6)
+    cw, cws = ingress.cond_windows(cond, 1, 5)
+    assert np.allclose(cw, g["lm_cond_win"], atol=1e-6) and np.allclose(cws, g["lm_cond_wins"], atol=1e-6)
+    # camera path
+    assert np.allclose(ingress.smooth_camera_path(g["poses_in"], 7), g["poses_smooth7"], atol=1e-9)
+    assert np.allclose(ingress.smooth_camera_path(g["poses_in"], 3), g["poses_smooth3"], atol=1e-9)
+    assert np.allclose(np.stack([utils.nerf_matrix_to_ngp(p, scale=4, offset=[0.1, -0.2, 0.3]) for p in g["poses_in"]]), g["ngp"], atol=1e-6)
+    # the dataset file format (pickled dict, data_gen/nerf/binarizer.py:175-199)
+    F = 4
+    ds = dict(H=32, W=32, focal=80.0, cx=16.0, cy=16.0, bg_img=(np.arange(32 * 32 * 3) % 256).astype(np.uint8).reshape(32, 32, 3),
+              idexp_lm3d_mean=g["lm_mean"], idexp_lm3d_std=g["lm_std"],
+              train_samples=[dict(c2w=g["poses_in"][i], idexp_lm3d_normalized_win=cond[i][None]) for i in range(F)],
+              val_samples=[dict(c2w=g["poses_in"][F + i], idexp_lm3d_normalized_win=cond[F + i][None]) for i in range(2)])
+    np.save(tmp_path / "trainval_dataset.npy", ds, allow_pickle=True)
+    inp = ingress.SequenceInputs.load(str(tmp_path), prefix="trainval", smooth_kernel=3)
+    assert inp.poses.shape == (F + 2, 4, 4) and inp.conds.shape == (F + 2, 1, 204) and inp.intrinsics == (80.0, 80.0, 16.0, 16.0)
+    assert inp.bg_img.max() <= 1.0 and inp.bg_img.shape == (32, 32, 3)
+    ref_poses = ingress.smooth_camera_path(np.stack([utils.nerf_matrix_to_ngp(p) for p in g["poses_in"][:F + 2]]), 3)
+    assert np.allclose(inp.poses, ref_poses, atol=1e-6)
+    poses, wins = inp.sequence(g["lm_in"], 2.5)
+    assert wins.shape == (9, 5, 1, 204) and np.allclose(wins, g["lm_cond_wins"], atol=1e-6)
+    assert poses.shape == (9, 4, 4) and np.array_equal(poses[6], inp.poses[0])           # camera path cycles
+    import pytest
+    with pytest.raises(ValueError):
+        ingress.SequenceInputs.load(str(tmp_path), prefix="test")
