@@ -468,6 +468,9 @@ static bool tc_mode_fused() {
     return mode == 1;
 }
 
+// kernels one precision-1 field evaluation launches (gpu_launches bookkeeping of gf_render_frame)
+int field_tc_kernel_count() { return tc_mode_fused() ? 1 : 2; }
+
 int field_tc_launch(const GfModel* model, const FieldTcIO& io, cudaStream_t st) {
     if (!tc_mode_fused()) return field_tc_split_launch(model, io, st);
     GfModel* m = const_cast<GfModel*>(model);

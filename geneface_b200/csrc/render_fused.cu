@@ -679,6 +679,7 @@ using namespace gf;
 
 namespace gf {
 int field_tc_launch(const GfModel* model, const FieldTcIO& io, cudaStream_t st);   // field_tc.cu
+int field_tc_kernel_count();                                                      // field_tc.cu
 }
 
 extern "C" {
@@ -964,6 +965,7 @@ GF_API int gf_render_frame(const GfModel* model, const GfFrame* f, const GfOut* 
         return r;
     };
 
+    const uint32_t field_kernels = f->precision == 0 ? 1u : (uint32_t)field_tc_kernel_count();
     // pass A: rounds covering exactly max_steps slots
     for (uint32_t before = 0; before < f->max_steps; before += chunk) {
         const uint32_t budget = (f->max_steps - before) < chunk ? (f->max_steps - before) : chunk;
@@ -973,7 +975,7 @@ GF_API int gf_render_frame(const GfModel* model, const GfFrame* f, const GfOut* 
         if ((rc = field())) return rc;
         ca.budget = budget; ca.budget_from_ctl = 0; ca.slots_before = before;
         k_composite_chunk<<<div_up(N, 128), 128, 0, st>>>(ca, w.st, w.sb, w.ctl);
-        launches += 3;
+        launches += 2 + field_kernels;
     }
     // schedule replay -> S_total; extra round with device-side budget
     k_schedule<<<1, 32, 0, st>>>(N, f->max_steps, w.ctl);
@@ -982,7 +984,7 @@ GF_API int gf_render_frame(const GfModel* model, const GfFrame* f, const GfOut* 
     if ((rc = field())) return rc;
     ca.budget = 0; ca.budget_from_ctl = 1; ca.slots_before = f->max_steps;
     k_composite_chunk<<<div_up(N, 128), 128, 0, st>>>(ca, w.st, w.sb, w.ctl);
-    launches += 4;
+    launches += 3 + field_kernels;
     if ((rc = check_launch("render_frame(rounds)"))) return rc;
 
     FinishArgs fa;
