@@ -120,6 +120,26 @@ __device__ __forceinline__ void stream_wait_mma(uint32_t bar_mma, uint32_t& phas
 #endif
 }
 
+// (experimental, -DGF_BIAS_IN_ACC=1) kernel A: instead of adding the per-frame bias in the ambient-L0 epilogue (128 FADD + 32 LDS per
+// row-tile), every consumer thread pre-loads it into its own accumulator lane right after its last read of the previous tile, and the
+// layer's first MMA accumulates.  Not used by the debug instantiation (whose stage-0 dump is defined as the pre-bias accumulator).
+#ifndef GF_BIAS_IN_ACC
+#define GF_BIAS_IN_ACC 0
+#endif
+__device__ __forceinline__ void preload_bias_to_acc(uint32_t t_d, const float* __restrict__ bias_smem) {
+    #pragma unroll 1
+    for (int c = 0; c < 8; c++) {
+        uint32_t p[16];
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_smem + 16 * c + 4 * q);
+            p[4 * q] = __float_as_uint(b.x); p[4 * q + 1] = __float_as_uint(b.y); p[4 * q + 2] = __float_as_uint(b.z); p[4 * q + 3] = __float_as_uint(b.w);
+        }
+        tmem_st16(t_d + 16 * c, p);
+    }
+    tmem_wait_st();
+}
+
 struct SpArgs {
     GridDesc grid;              // A: 3-D position grid; B: 2-D ambient grid
     float bound, inv2b;
@@ -332,20 +352,22 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
         const uint32_t bar_mma = sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT + stream);
         const uint32_t w_addr = sbase;
         const bool leader = row == 0;
+        constexpr bool PRELOAD = GF_BIAS_IN_ACC && !DBG;
         uint32_t phase = 0;
+        if (PRELOAD) preload_bias_to_acc(t_d, bias_cond);
         for (uint32_t j = stream; j < my_tiles; j += 2) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
             const uint32_t i = tile * 128 + row;
             float* dbg = (DBG && a.dbg && tile == 0) ? a.dbg + (size_t)row * 144 : nullptr;   // DBG = false: folds every dump away
             const uint32_t f_addr = sbase + L::F + slot * SP_TILE_BYTES;
             tc_fence_before();
-            bar_named(1 + stream, 128);                                   // previous tile's accumulator reads are done
+            bar_named(1 + stream, 128);                                   // previous tile's accumulator reads (and bias pre-loads) are done
             if (leader) {
                 mbar_wait(bar_full + 8 * slot, n & 1);
                 tc_fence_after();
                 // split precision: F_hi W_hi + F_lo W_hi + F_hi W_lo  (K = 32 each)
                 #pragma unroll
-                for (int k = 0; k < 2; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WA_A0 + 32 * k), idesc_f16(128), k);
+                for (int k = 0; k < 2; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WA_A0 + 32 * k), idesc_f16(128), PRELOAD ? 1 : k);
                 #pragma unroll
                 for (int k = 0; k < 2; k++) mma_ss(m_d, smem_desc(f_addr + 64 + 32 * k), smem_desc(w_addr + WA_A0 + 32 * k), idesc_f16(128), 1);
                 #pragma unroll
@@ -355,7 +377,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
             tc_fence_after();
             if (leader) mbar_arrive(bar_empty + 8 * slot);                // the feature tile has been consumed
-            epilogue_relu_to_A_n<true, 4>(t_d, t_d + SP_TM_AHI, t_d + SP_TM_ALO, 0, bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);
+            epilogue_relu_to_A_n<true, 4>(t_d, t_d + SP_TM_AHI, t_d + SP_TM_ALO, 0, PRELOAD ? nullptr : bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);
             tc_fence_before();
             bar_named(1 + stream, 128);
             if (leader) {
@@ -391,6 +413,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
                 }
             }
             const float s0 = acc0.x + acc0.y, s1 = acc1.x + acc1.y;
+            if (PRELOAD) preload_bias_to_acc(t_d, bias_cond);            // own lane only: no other thread reads or writes it
             if (dbg) { dbg[2 * 128 * 144 + 0] = s0; dbg[2 * 128 * 144 + 1] = s1; }
             if (i < M) a.io.amb_pos[i] = make_float2(tanhf(s0), tanhf(s1));
         }
