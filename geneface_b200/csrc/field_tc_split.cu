@@ -123,6 +123,11 @@ __device__ __forceinline__ void stream_wait_mma(uint32_t bar_mma, uint32_t& phas
 // (experimental, -DGF_BIAS_IN_ACC=1) kernel A: instead of adding the per-frame bias in the ambient-L0 epilogue (128 FADD + 32 LDS per
 // row-tile), every consumer thread pre-loads it into its own accumulator lane right after its last read of the previous tile, and the
 // layer's first MMA accumulates.  Not used by the debug instantiation (whose stage-0 dump is defined as the pre-bias accumulator).
+// (experimental, -DGF_SPECIALIZE_GRID=1) launch instantiations with the smoothstep / hash code compiled out for models whose grids are
+// linear + tiled (the reference's configuration); measured motivation: ~14 of ~60 instructions per 2-D level are issued predicated-off.
+#ifndef GF_SPECIALIZE_GRID
+#define GF_SPECIALIZE_GRID 0
+#endif
 #ifndef GF_BIAS_IN_ACC
 #define GF_BIAS_IN_ACC 0
 #endif
@@ -192,7 +197,9 @@ __device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, cons
 // z+1 plane only when it exists.  Interpolation is bilinear per z-plane, then a lerp in z (the fp32 result differs from the
 // reference's corner-order sum by rounding only; it is rounded to fp16 right after).
 // ALLFLAT: every level of the batch drops z and is not hashed -> only the 4 corners of the z0 plane exist (uniform fast path).
-template <bool ALLFLAT>
+// PLAIN: the model's grids are linear-interpolated and not hashed (gridtype tiled): the smoothstep and hash code is compiled out
+// instead of being issued predicated-off (experimental specialisation, see GF_SPECIALIZE_GRID).
+template <bool ALLFLAT, bool PLAIN>
 __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x, float y, float z, float2 (&out)[4]) {
     float fx[4], fy[4], fz[4];
     float2 v[4][8];
@@ -203,11 +210,11 @@ __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x,
         float px = __fmaf_rn(x, scale, 0.5f), py = __fmaf_rn(y, scale, 0.5f), pz = __fmaf_rn(z, scale, 0.5f);
         const uint32_t gx = (uint32_t)floorf(px), gy = (uint32_t)floorf(py), gz = (uint32_t)floorf(pz);
         px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy); pz = __fsub_rn(pz, (float)gz);
-        if (g.interp == 1) { px = smooth_(px); py = smooth_(py); pz = smooth_(pz); }
+        if (!PLAIN && g.interp == 1) { px = smooth_(px); py = smooth_(py); pz = smooth_(pz); }
         fx[i] = px; fy[i] = py; fz[i] = pz;
         const float2* __restrict__ tab = g.lbase[l];
         const uint32_t mask = g.lv.mask[l], sy = g.lv.sy[l], sz = g.lv.sz[l];
-        const bool hashed = !ALLFLAT && g.lv.hashed[l] != 0;
+        const bool hashed = !ALLFLAT && !PLAIN && g.lv.hashed[l] != 0;
         const bool has_z = !ALLFLAT && (hashed || sz != 0);
         uint32_t idx[8];
         if (ALLFLAT) {
@@ -246,6 +253,7 @@ __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x,
 }
 
 // 2-D ambient grid, 8 consecutive levels from l0 (32 gathers in flight)
+template <bool PLAIN>
 __device__ __forceinline__ void gather2_dyn8(const GridDesc& g, int l0, float x, float y, float2 (&out)[8]) {
     const bool oob = x < 0 || x > 1 || y < 0 || y > 1;            // tanh output mapped to [0,1]: cannot happen, kept for safety
     if (oob) { x = 0.5f; y = 0.5f; }
@@ -258,12 +266,12 @@ __device__ __forceinline__ void gather2_dyn8(const GridDesc& g, int l0, float x,
         float px = __fmaf_rn(x, scale, 0.5f), py = __fmaf_rn(y, scale, 0.5f);
         const uint32_t gx = (uint32_t)floorf(px), gy = (uint32_t)floorf(py);
         px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy);
-        if (g.interp == 1) { px = smooth_(px); py = smooth_(py); }
+        if (!PLAIN && g.interp == 1) { px = smooth_(px); py = smooth_(py); }
         fx[i] = px; fy[i] = py;
         const float2* __restrict__ tab = g.lbase[l];
         const uint32_t mask = g.lv.mask[l], sy = g.lv.sy[l];
         uint32_t idx[4];
-        if (g.lv.hashed[l]) {
+        if (!PLAIN && g.lv.hashed[l]) {
             const uint32_t y0 = gy * HASH_P1, y1 = y0 + HASH_P1;
             idx[0] = gx ^ y0; idx[1] = (gx + 1) ^ y0; idx[2] = gx ^ y1; idx[3] = (gx + 1) ^ y1;
         } else {
@@ -283,7 +291,7 @@ __device__ __forceinline__ void gather2_dyn8(const GridDesc& g, int l0, float x,
     }
 }
 
-template <bool DBG>
+template <bool DBG, bool PLAIN>
 __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
     using L = SpSmem<WA_TOTAL>;
     extern __shared__ uint8_t smem_raw[];
@@ -331,8 +339,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             for (uint32_t b = 0; b < 2; b++) {
                 const uint32_t u = half + 2 * b;
                 float2 f[4];
-                if ((flat_units >> u) & 1) gather3_dyn4<true>(a.grid, 4 * u, ux, uy, uz, f);
-                else gather3_dyn4<false>(a.grid, 4 * u, ux, uy, uz, f);
+                if ((flat_units >> u) & 1) gather3_dyn4<true, PLAIN>(a.grid, 4 * u, ux, uy, uz, f);
+                else gather3_dyn4<false, PLAIN>(a.grid, 4 * u, ux, uy, uz, f);
                 if (oob) { f[0] = f[1] = f[2] = f[3] = make_float2(0.f, 0.f); }
                 const uint4 hi = make_uint4(pack_h2(f[0].x, f[0].y), pack_h2(f[1].x, f[1].y), pack_h2(f[2].x, f[2].y), pack_h2(f[3].x, f[3].y));
                 *reinterpret_cast<uint4*>(F + sw128(row, u)) = hi;
@@ -426,7 +434,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
 // ======================================================================================================================
 // kernel B: features + 2-D gather -> sigma / colour
 // ======================================================================================================================
-template <bool DBG>
+template <bool DBG, bool PLAIN>
 __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
     using L = SpSmem<WB2_TOTAL>;
     extern __shared__ uint8_t smem_raw[];
@@ -479,7 +487,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             *reinterpret_cast<uint4*>(F + sw128(row, 2 * half + 1)) = hi1;
             if (half == 1) reinterpret_cast<float4*>(smem + L::DIR)[slot * 128 + row] = dir;
             float2 f[8];
-            gather2_dyn8(a.grid, 8 * half, vx, vy, f);
+            gather2_dyn8<PLAIN>(a.grid, 8 * half, vx, vy, f);
             #pragma unroll
             for (int u = 0; u < 2; u++)
                 *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * half + u)) =
@@ -614,10 +622,14 @@ static int ensure_split_pack(GfModel* m, cudaStream_t st) {
     k_tc_pack_split<<<(144 * 128 + 255) / 256, 256, 0, st>>>(s, img, img + WA_TOTAL);
     int rc = check_launch("tc split pack");
     if (rc) { cudaFree(img); return rc; }
-    if (cudaFuncSetAttribute(k_tc_amb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_tc_amb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_tc_sigcol<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_tc_sigcol<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_tc_amb<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_amb<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_sigcol<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_sigcol<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
+#if GF_SPECIALIZE_GRID
+        cudaFuncSetAttribute(k_tc_amb<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_sigcol<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
+#endif
         cudaMemcpyAsync(m->w_amb2_host, m->w + m->dev.a_w2, sizeof(float) * 256, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) {
         cudaGetLastError();
@@ -660,15 +672,25 @@ int field_tc_split_launch(const GfModel* model, const FieldTcIO& io_in, cudaStre
     a.wimg = (const uint8_t*)m->tc2_blob;
     a.bias = io.bias_amb;
     memcpy(a.w_amb2, m->w_amb2_host, sizeof(a.w_amb2));
-    if (a.dbg) k_tc_amb<true><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
-    else k_tc_amb<false><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
+    // plain = no smoothstep, no hashed level in either grid: the specialised instantiations may be used (when compiled in)
+    bool plain = model->dev.pos.interp == 0 && model->dev.amb.interp == 0;
+    for (int l = 0; l < 16; l++) plain = plain && model->dev.pos.lv.hashed[l] == 0 && model->dev.amb.lv.hashed[l] == 0;
+    (void)plain;
+    if (a.dbg) k_tc_amb<true, false><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
+#if GF_SPECIALIZE_GRID
+    else if (plain) k_tc_amb<false, true><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
+#endif
+    else k_tc_amb<false, false><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
     rc = check_launch("field_tc_split(amb)");
     if (rc) return rc;
     a.grid = model->dev.amb;
     a.wimg = (const uint8_t*)m->tc2_blob + WA_TOTAL;
     a.bias = model->dev.ind ? model->dev.w + model->dev.c_bind : nullptr;
-    if (a.dbg) k_tc_sigcol<true><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
-    else k_tc_sigcol<false><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
+    if (a.dbg) k_tc_sigcol<true, false><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
+#if GF_SPECIALIZE_GRID
+    else if (plain) k_tc_sigcol<false, true><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
+#endif
+    else k_tc_sigcol<false, false><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
     return check_launch("field_tc_split(sigcol)");
 }
 
