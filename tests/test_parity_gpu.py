@@ -646,3 +646,24 @@ def test_density_grid_maintenance_vs_oracle(monkeypatch):
     assert abs(model.mean_density - mean) < 1e-6 * max(1.0, mean)
     thresh = min(mean, model.density_thresh)
     assert np.array_equal(model.density_bitfield.cpu().numpy(), cpu_ops.packbits(got, thresh))
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first execution pending: written after this round's GPU budget was spent (hash / smoothstep grids through the "
+                                        "fused field kernels had only been exercised through the fine-grained encoder ops)")
+@pytest.mark.parametrize("grid_type,interp", [("hashgrid", "linear"), ("tiledgrid", "smoothstep"), ("hashgrid", "smoothstep")])
+def test_fused_field_on_hash_and_smoothstep_grids(grid_type, interp):
+    """The reference configuration is tiled + linear; the fused field kernels also implement the hashed index (gridencoder.cu:54-84) and
+    smoothstep interpolation (:127-131).  Checked against the torch module forward on the fine-grained encoder ops (which are themselves
+    pinned against the compiled reference for every gridtype / interpolation)."""
+    from geneface_b200 import synthetic
+    model, hp = synthetic.build_model(torso=False, bitfield='S', seed=2, grid_type=grid_type, grid_interpolation_type=interp)
+    xyz, d = scenes.field_samples(3000, seed=6, bound=1.0)
+    cond_feat = torch.randn(64, generator=torch.Generator().manual_seed(2)).cuda()
+    with torch.no_grad():
+        s_t, c_t, a_t = model(cu(xyz), cu(d), cond_feat.view(1, -1), model.individual_embeddings[0])
+    for prec, rel in (("fp32", 1e-3), ("fp16", 2e-3)):
+        sig, rgb, amb = model.field_forward(cu(xyz), cu(d), cond_feat, precision=prec)
+        assert_close(amb.cpu().numpy(), a_t.cpu().numpy(), rel=1e-3, abs_=2e-5, what=f"ambient_pos {prec}")
+        assert_close(sig.cpu().numpy(), s_t.cpu().numpy(), rel=rel, abs_=1e-6, what=f"sigma {prec}")
+        assert_close(rgb.cpu().numpy(), c_t.cpu().numpy(), rel=1e-3, abs_=2e-4, what=f"rgb {prec}")
