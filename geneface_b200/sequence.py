@@ -57,7 +57,8 @@ class SequenceRenderer:
         n = end - start
         N = self.H * self.W
         host = out_rgb8 if out_rgb8 is not None else torch.empty(n, self.H, self.W, 3, dtype=torch.uint8).pin_memory()
-        dev_rgb8 = [torch.empty(N, 3, dtype=torch.uint8, device='cuda') for _ in range(2)]
+        dev = next(self.model.parameters()).device
+        dev_rgb8 = [torch.empty(N, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
         copy_stream = torch.cuda.Stream()
         done = [None, None]
         landed, flushed = [], 0                    # per-frame "in host memory" events; frames already handed to the sink

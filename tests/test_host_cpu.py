@@ -189,3 +189,65 @@ def test_ingress_matches_the_reference_golden(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         ingress.SequenceInputs.load(str(tmp_path), prefix="test")
+
+
+def test_sequence_renderer_pipeline_logic_with_a_fake_device(monkeypatch):
+    """The frame pipeline of sequence.SequenceRenderer (double-buffered device frames, copy stream, per-frame 'landed' events, sink two
+    frames behind) exercised on the CPU with stand-ins for the CUDA stream/event objects and for the fused renderer."""
+    import contextlib
+    from geneface_b200 import sequence
+
+    log = []
+
+    class FakeEvent:
+        def __init__(self, *a, **k):
+            self.recorded = False
+
+        def record(self, stream=None):
+            self.recorded = True
+
+        def synchronize(self):
+            assert self.recorded, "synchronised an event that was never recorded"
+            log.append("sync")
+
+    class FakeStream:
+        def wait_event(self, ev):
+            assert ev.recorded
+
+        def synchronize(self):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: FakeStream())
+
+    class FakeModel(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+
+        def cal_cond_feat(self, cond):
+            return cond.sum().view(1)
+
+        def render_fused(self, cond_feat, H, W, pose=None, out=None, **kw):
+            out['rgb8'].fill_(int(pose[0, 3].item()) % 251)          # frame content = a function of the pose
+            return out
+
+    H = W = 4
+    F = 7
+    poses = torch.eye(4).repeat(F, 1, 1)
+    poses[:, 0, 3] = torch.arange(F).float() + 10
+    conds = torch.randn(F, 5, 1, 204)
+    host = torch.zeros(F - 2, H, W, 3, dtype=torch.uint8)
+    seq = sequence.SequenceRenderer(FakeModel(), H, W, (1.0, 1.0, 2.0, 2.0), torso=False)
+    sunk = []
+    out = seq.render(poses, conds, None, 2, F, out_rgb8=host, sink=lambda idx, fr: sunk.append((idx, int(fr[0, 0, 0]))))
+    assert out is host
+    assert [int(host[k, 0, 0, 0]) for k in range(F - 2)] == [12, 13, 14, 15, 16]
+    assert sunk == [(2, 12), (3, 13), (4, 14), (5, 15), (6, 16)]           # in order, every frame exactly once, right content
+    assert log.count("sync") == F - 2
+    # without a sink nothing is synchronised per frame
+    log.clear()
+    seq.render(poses, conds, None, 0, 3, out_rgb8=torch.zeros(3, H, W, 3, dtype=torch.uint8))
+    assert log == []
