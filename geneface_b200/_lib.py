@@ -12,10 +12,13 @@ import sys
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
-_SO = os.path.join(_PKG, "libgfrender.so")
+# GF_LIBGFRENDER selects another build of the same library (experiment variants built by `build(out=..., extra=...)`,
+# e.g. scripts/build_variants.py); the default is the in-tree geneface_b200/libgfrender.so.
+_SO = os.environ.get("GF_LIBGFRENDER") or os.path.join(_PKG, "libgfrender.so")
+_VARIANT = bool(os.environ.get("GF_LIBGFRENDER"))
 _INCLUDE = os.path.join(os.path.dirname(_PKG), "include")
 
-SOURCES = ["api.cu", "raymarch_ops.cu", "encoders.cu", "render_fused.cu", "field_tc.cu", "field_tc_split.cu", "adnerf_ops.cu"]
+SOURCES = ["api.cu", "raymarch_ops.cu", "encoders.cu", "render_fused.cu", "field_tc_split.cu", "adnerf_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -30,6 +33,10 @@ def _nvcc():
 
 
 def _stale():
+    if _VARIANT:
+        if not os.path.exists(_SO):
+            raise RuntimeError("GF_LIBGFRENDER=%s does not exist" % _SO)
+        return False
     if not os.path.exists(_SO):
         return True
     t = os.path.getmtime(_SO)
@@ -37,26 +44,31 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """nvcc-compile every .cu under csrc/ for sm_100a into geneface_b200/libgfrender.so (in-tree)."""
-    if not force and not _stale():
-        return _SO
+def build(force=False, verbose=False, out=None, extra=None):
+    """nvcc-compile every .cu under csrc/ for sm_100a into geneface_b200/libgfrender.so (in-tree).
+    out / extra: build an experiment variant (extra nvcc flags such as -DGF_...=1) into another .so with its own object directory."""
+    so = out or os.path.join(_PKG, "libgfrender.so")
+    if out is None and not force and not _stale():
+        return so
     nvcc = _nvcc()
     objs = []
     procs = []
-    os.makedirs(os.path.join(_PKG, "build"), exist_ok=True)
+    bdir = os.path.join(_PKG, "build") if out is None else os.path.splitext(out)[0] + "_obj"
+    os.makedirs(bdir, exist_ok=True)
+    force = force or out is not None
+    extra = list(extra or []) + os.environ.get("GF_NVCC_EXTRA", "").split()        # GF_NVCC_EXTRA: experiment switches (-D...)
     for src in SOURCES:
         path = os.path.join(_CSRC, src)
         if not os.path.exists(path):
             raise RuntimeError("missing CUDA source %s" % path)
-        obj = os.path.join(_PKG, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
         objs.append(obj)
         if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(
                 os.path.getmtime(path), os.path.getmtime(os.path.join(_CSRC, "gf_common.cuh")),
                 os.path.getmtime(os.path.join(_INCLUDE, "gfrender.h")),
                 *[os.path.getmtime(os.path.join(_CSRC, h)) for h in os.listdir(_CSRC) if h.endswith(".cuh")]):
             continue
-        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("GF_NVCC_EXTRA", "").split() + ["-I", _INCLUDE, "-c", path, "-o", obj]   # GF_NVCC_EXTRA: experiment switches (-D...)
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", _INCLUDE, "-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -67,11 +79,11 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
-    cmd = [nvcc, "-shared", "-o", _SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", so] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stdout)
-    return _SO
+    return so
 
 
 _lib = None
@@ -113,7 +125,8 @@ _SIGS = {
     "gf_model_packed_bytes": [c_vp],
     "gf_render_workspace_bytes": [c_u32],
     "gf_render_frame": [c_vp, c_vp, c_vp, c_vp, c_u64, c_vp],
-    "gf_field_forward": [c_vp, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_u32, c_vp],
+    "gf_field_forward": [c_vp, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_u32, c_vp, c_u64, c_vp],
+    "gf_field_workspace_bytes": [c_u32, c_u32],
     "gf_tc_debug": [c_vp, c_vp],
     "gf_profile_enable": [c_vp, c_int],
     "gf_profile_field_ms": [c_vp, c_vp, c_vp],
@@ -122,7 +135,7 @@ _SIGS = {
     "gf_device_ok": [],
 }
 _RESTYPE = {"gf_last_error": ctypes.c_char_p, "gf_model_destroy": None, "gf_model_packed_bytes": c_u64,
-            "gf_render_workspace_bytes": c_u64}
+            "gf_render_workspace_bytes": c_u64, "gf_field_workspace_bytes": c_u64}
 
 EXPORTS = sorted(_SIGS)
 
@@ -136,8 +149,8 @@ def lib():
         try:
             build()
         except Exception as e:  # noqa: BLE001
-            if not os.path.exists(_SO):
-                raise RuntimeError("libgfrender.so is not built and could not be built: %s" % e)
+            # never run an old binary against newer ctypes signatures: a stale library that cannot be rebuilt is an error
+            raise RuntimeError("libgfrender.so is %s and could not be rebuilt: %s" % ("stale" if os.path.exists(_SO) else "not built", e))
     try:
         L = ctypes.CDLL(_SO)
     except OSError as e:

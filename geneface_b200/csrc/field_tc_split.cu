@@ -1,11 +1,10 @@
-// libgfrender: warp-specialised, two-kernel tcgen05 field pipeline (precision = 1, default mode).
+// libgfrender: warp-specialised, two-kernel tcgen05 field pipeline (precision = 1, the default).
 //
-// The single fused kernel (field_tc.cu) serialises, per tile, {3-D gather -> 2 MMA layers -> 2-D gather -> 5 MMA layers}:
-// the gathers (L1/L2 latency) and the MMA chain (tensor latency) cannot overlap because only two tiles fit in tensor
-// memory (a 128-row tile needs 128 accumulator + 64..128 operand columns of the 512) and the 184 KB of weights leave no
-// shared memory for look-ahead feature tiles.  Splitting the field at the ambient coordinate halves the weights each
-// kernel keeps resident, which buys a 6-deep ring of feature tiles and lets DEDICATED PRODUCER WARPS gather ahead while
-// two consumer streams run the MMA chain back to back:
+// One 128-sample tile needs, per layer, 128 accumulator + 64..128 operand columns of the SM's 512 tensor-memory columns, so only two
+// tiles can be inside the MLP chain at once, and the 184 KB of fp16 weights of the whole field would leave no shared memory to gather
+// ahead (the single-kernel variant of round 1 alternated gathers and MMAs: 16.8 ms/frame, issue slots 37 % busy; removed in round 2).
+// Splitting the field at the ambient coordinate halves the weights each kernel keeps resident, which buys a 6-deep ring of feature
+// tiles and lets DEDICATED PRODUCER WARPS gather ahead while two consumer streams run the MMA chain back to back:
 //
 //   k_tc_amb     producers (8 warps): 3-D grid gather -> fp16 hi/lo feature tile in the smem ring (+ hi copy to HBM)
 //                consumers (2 x 4 warps, one thread per sample row = TMEM lane):
@@ -17,7 +16,7 @@
 // Producer -> consumer hand-off: one `full` mbarrier per ring slot (256 producer arrivals, generic->async proxy fence before
 // the arrive), one `empty` mbarrier per slot (arrived by the stream leader once the tcgen05.commit of the last MMA reading
 // the slot has completed).  Extra HBM traffic: 64 + 8 B/sample written and read once (4.8 GB/frame at 512x512x128, <10 %
-// of the algorithmic gather bytes); everything else about the arithmetic is identical to field_tc.cu.
+// of the algorithmic gather bytes).
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -189,7 +188,7 @@ __device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, cons
 // ======================================================================================================================
 // ---- gathers with a RUN-TIME level index ------------------------------------------------------------------------------
 // The producers' code must stay small: four instruction streams (2 producer + 2 consumer warps) share each scheduler's
-// ~6 KB L0 / the SM's 32 KB L1.5 instruction cache, and the fully unrolled per-level code of field_tc.cu (72 KB of SASS)
+// ~6 KB L0 / the SM's 32 KB L1.5 instruction cache, and the fully unrolled per-level code of the removed single-kernel variant (72 KB of SASS)
 // left the producer warps starved for instructions (ncu: 45 % of their stall samples were no_instruction).  Here ONE
 // copy of a 4-level batch serves both halves and both batches; level constants are indexed loads from the constant bank.
 //
@@ -299,6 +298,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
     const uint32_t sbase = smem_u32(smem);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t M = a.io.M_dev ? *a.io.M_dev : a.io.M_host;
+    if (M == 0) return;                      // e.g. the extra round of a frame whose budget is 0: skip weight staging / TMEM allocation
     const uint32_t cuts[4] = {0, WA_A1H, WA_A1L, WA_TOTAL};
     const uint32_t tmem_base = sp_setup<WA_TOTAL>(smem, sbase, a, cuts, 3);
     const float* bias_cond = reinterpret_cast<const float*>(smem + L::BIAS);
@@ -442,6 +442,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
     const uint32_t sbase = smem_u32(smem);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t M = a.io.M_dev ? *a.io.M_dev : a.io.M_host;
+    if (M == 0) return;
     const uint32_t cuts[5] = {0, WB2_SIG1, WB2_MRG, WB2_COL1, WB2_TOTAL};
     const uint32_t tmem_base = sp_setup<WB2_TOTAL>(smem, sbase, a, cuts, 4);
     const float* bias_ind = reinterpret_cast<const float*>(smem + L::BIAS);
@@ -606,13 +607,12 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
 // ======================================================================================================================
 // host
 // ======================================================================================================================
-static int ensure_split_pack(GfModel* m, cudaStream_t st) {
-    if (m->tc2_blob) return GF_OK;
+// Builds the fp16 weight images of both kernels; called ONCE from gf_model_create (nothing is packed lazily on the frame path, so
+// gf_render_frame never allocates or synchronises and can be captured into a CUDA graph).  Models outside the tcgen05 envelope
+// (hidden_dim / geo_feat_dim != 128) simply have no image: precision = 1 then returns GF_ERR_UNSUPPORTED.
+int field_tc_pack(GfModel* m, cudaStream_t st) {
     const GfModelDesc& d = m->desc;
-    if (d.hidden_dim != 128 || d.geo_feat_dim != 128) {
-        set_error("precision=1 (tcgen05) supports hidden_dim == 128 and geo_feat_dim == 128 only; use precision=0");
-        return GF_ERR_UNSUPPORTED;
-    }
+    if (d.hidden_dim != 128 || d.geo_feat_dim != 128) return GF_OK;
     uint8_t* img = nullptr;
     if (cudaMalloc(&img, WA_TOTAL + WB2_TOTAL) != cudaSuccess) { cudaGetLastError(); set_error("tc pack: cudaMalloc failed"); return GF_ERR_CUDA; }
     cudaMemsetAsync(img, 0, WA_TOTAL + WB2_TOTAL, st);
@@ -641,23 +641,18 @@ static int ensure_split_pack(GfModel* m, cudaStream_t st) {
     return GF_OK;
 }
 
-int field_tc_split_launch(const GfModel* model, const FieldTcIO& io_in, cudaStream_t st) {
-    GfModel* m = const_cast<GfModel*>(model);
-    int rc = ensure_split_pack(m, st);
-    if (rc) return rc;
-    FieldTcIO io = io_in;
-    if (!io.feat_hi || !io.amb_pos) {
-        // stand-alone field evaluation (gf_field_forward): model-owned, grow-only scratch
-        if (io.M_dev) { set_error("field_tc_split: device-side sample count needs caller scratch"); return GF_ERR_INVALID; }
-        const size_t need = (size_t)io.M_host * (64 + 8) + 256;
-        if (m->tc_scratch_bytes < need) {
-            if (m->tc_scratch) { cudaStreamSynchronize(st); cudaFree(m->tc_scratch); m->tc_scratch = nullptr; m->tc_scratch_bytes = 0; }
-            if (cudaMalloc(&m->tc_scratch, need) != cudaSuccess) { cudaGetLastError(); set_error("field_tc_split: scratch cudaMalloc failed"); return GF_ERR_CUDA; }
-            m->tc_scratch_bytes = need;
-        }
-        io.feat_hi = reinterpret_cast<uint4*>(m->tc_scratch);
-        io.amb_pos = reinterpret_cast<float2*>((char*)m->tc_scratch + (((size_t)io.M_host * 64 + 255) & ~size_t(255)));
+// bytes of caller-owned scratch one stand-alone field evaluation of M samples needs (fp16 position features + ambient coordinates)
+size_t field_tc_scratch_bytes(uint32_t M) { return (((size_t)M * 64 + 255) & ~size_t(255)) + (size_t)M * 8 + 256; }
+
+int field_tc_kernel_count() { return 2; }
+
+int field_tc_launch(const GfModel* model, const FieldTcIO& io_in, cudaStream_t st) {
+    if (!model->tc2_blob) {
+        set_error("precision=1 (tcgen05) supports hidden_dim == 128 and geo_feat_dim == 128 only; use precision=0");
+        return GF_ERR_UNSUPPORTED;
     }
+    const FieldTcIO& io = io_in;
+    if (!io.feat_hi || !io.amb_pos) { set_error("field_tc: the feature / ambient-coordinate scratch is missing"); return GF_ERR_INVALID; }
     uint32_t grid = (uint32_t)model->num_sms;
     if (!io.M_dev) {
         const uint32_t tiles = (io.M_host + 127) / 128;
@@ -667,11 +662,11 @@ int field_tc_split_launch(const GfModel* model, const FieldTcIO& io_in, cudaStre
     memset(&a, 0, sizeof(a));
     a.bound = model->dev.bound; a.inv2b = 0.5f / model->dev.bound;
     a.io = io;
-    a.dbg = m->tc_dbg;
+    a.dbg = model->tc_dbg;
     a.grid = model->dev.pos;
-    a.wimg = (const uint8_t*)m->tc2_blob;
+    a.wimg = (const uint8_t*)model->tc2_blob;
     a.bias = io.bias_amb;
-    memcpy(a.w_amb2, m->w_amb2_host, sizeof(a.w_amb2));
+    memcpy(a.w_amb2, model->w_amb2_host, sizeof(a.w_amb2));
     // plain = no smoothstep, no hashed level in either grid: the specialised instantiations may be used (when compiled in)
     bool plain = model->dev.pos.interp == 0 && model->dev.amb.interp == 0;
     for (int l = 0; l < 16; l++) plain = plain && model->dev.pos.lv.hashed[l] == 0 && model->dev.amb.lv.hashed[l] == 0;
@@ -681,10 +676,10 @@ int field_tc_split_launch(const GfModel* model, const FieldTcIO& io_in, cudaStre
     else if (plain) k_tc_amb<false, true><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
 #endif
     else k_tc_amb<false, false><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
-    rc = check_launch("field_tc_split(amb)");
+    const int rc = check_launch("field_tc_split(amb)");
     if (rc) return rc;
     a.grid = model->dev.amb;
-    a.wimg = (const uint8_t*)m->tc2_blob + WA_TOTAL;
+    a.wimg = (const uint8_t*)model->tc2_blob + WA_TOTAL;
     a.bias = model->dev.ind ? model->dev.w + model->dev.c_bind : nullptr;
     if (a.dbg) k_tc_sigcol<true, false><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
 #if GF_SPECIALIZE_GRID
@@ -695,3 +690,13 @@ int field_tc_split_launch(const GfModel* model, const FieldTcIO& io_in, cudaStre
 }
 
 }  // namespace gf
+
+extern "C" {
+// Diagnostics: make the next precision-1 launches dump the fp32 accumulators of tile 0 after each MMA stage into dbg
+// (device float[9*128*144]); pass NULL to switch it off.  Used by tests/test_parity_gpu.py.
+GF_API int gf_tc_debug(GfModel* model, float* dbg) {
+    if (!model) return GF_ERR_INVALID;
+    model->tc_dbg = dbg;
+    return GF_OK;
+}
+}

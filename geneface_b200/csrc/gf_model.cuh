@@ -1,4 +1,4 @@
-// Host/device structs shared by render_fused.cu and field_tc.cu.
+// Host/device structs shared by render_fused.cu and field_tc_split.cu.
 #pragma once
 #include "gf_field.cuh"
 
@@ -36,6 +36,7 @@ struct RayState {
     float *wsum, *depth, *img;
     uint8_t* alive;
     int* nsamp;
+    int* term;                // termination slot (1-based) of a dead ray, 0 while alive
     uint32_t *seg_off, *seg_cnt;
 };
 
@@ -53,6 +54,7 @@ struct RayInit {
     float fx, fy, cx, cy;
     float aabb[6];
     float min_near;
+    const float* dyn;          // GfFrame.dyn or null
 };
 
 struct MarchArgs {
@@ -87,10 +89,11 @@ struct FinishArgs {
     float *out_torso_alpha, *out_torso_rgb;
     float *rgb_map, *depth_map, *weights_sum;
     int32_t* n_samples;
+    int32_t* term_slot;
     uint8_t* rgb8;
 };
 
-// IO of the tensor-core field kernel (field_tc.cu); mirrors FieldIO of the fp32 kernel.
+// IO of the tensor-core field kernels (field_tc_split.cu); mirrors FieldIO of the fp32 kernel.
 struct FieldTcIO {
     const float4* pos4;
     const float* rays_d;
@@ -119,13 +122,8 @@ struct GfModel {
     gf::ModelDev dev;
     float* w;               // packed fp32 blob (device)
     size_t w_floats;
-    float* scratch_bias;    // device float[256] for gf_field_forward
-    void* tc_blob;          // packed fp16 tensor-core weights (device), built lazily
-    size_t tc_bytes;
-    float w_amb2_host[256]; // fp32 ambient output layer [2][128] (host copy, passed by value to k_field_tc)
-    void* tc2_blob;         // weight images of the split pipeline (device)
-    void* tc_scratch;       // grow-only scratch for gf_field_forward in split mode
-    size_t tc_scratch_bytes;
+    float w_amb2_host[256]; // fp32 ambient output layer [2][128] (host copy, passed by value to k_tc_amb)
+    void* tc2_blob;         // fp16 weight images of the two tcgen05 kernels (device), built in gf_model_create; null outside the envelope
     float* tc_dbg;          // diagnostics buffer for the tcgen05 kernel (gf_tc_debug) or null
     int num_sms;
     int profiling, ev_used;

@@ -11,7 +11,7 @@
 //   R rounds of        k_march_chunk     each live ray emits its next <=chunk occupied samples
 //                                        into a DENSE sample list (warp-aggregated allocation)
 //                      k_field_*         field evaluation over the dense list (fp32 SIMT here,
-//                                        fp16 tcgen05 in field_tc.cu)
+//                                        fp16 tcgen05 in field_tc_split.cu)
 //                      k_composite_chunk per-ray front-to-back compositing, termination, histogram
 //   k_schedule         replays the reference's host loop n_step = clamp(N // n_alive, 1, 8) from the
 //                      termination histogram -> S_total in [max_steps, max_steps+7]
@@ -92,6 +92,7 @@ struct FrameSetup {
     const float* cond_feat;   // [cond]
     float torso_pose[6];
     int has_torso;
+    const float* dyn;         // GfFrame.dyn (device float[22]) or null
 };
 
 // block 0: ambient bias[h] = sum_c W_a0[h][32 + c] * cond[c]     (radnerf.py:80,84 folded)
@@ -114,11 +115,13 @@ __global__ void k_frame_setup(ModelDev m, FrameSetup fs, float* __restrict__ bia
         // freqencoder.cu:30-58 with D=6, deg=4
         const int c = t;
         float v;
-        if (c < 6) v = fs.torso_pose[c];
+        const int d = c % 6;
+        const float pd = fs.dyn ? __ldg(fs.dyn + 16 + d) : fs.torso_pose[d];
+        if (c < 6) v = pd;
         else {
-            const int col = c / 6 - 1, d = c % 6, freq = col / 2;
+            const int col = c / 6 - 1, freq = col / 2;
             const float phase = (float)(col % 2) * (3.141592653589793f / 2);
-            v = __sinf(__fadd_rn(scalbnf(fs.torso_pose[d], freq), phase));
+            v = __sinf(__fadd_rn(scalbnf(pd, freq), phase));
         }
         cst[c] = v;
     } else if (t < 54 + m.t_ind) cst[t] = m.t_code ? __ldg(m.t_code + (t - 54)) : 0.f;
@@ -152,16 +155,25 @@ __global__ void k_rays_init(RayInit ri, RayState st) {
         dx = ri.rays_d[3 * (size_t)n]; dy = ri.rays_d[3 * (size_t)n + 1]; dz = ri.rays_d[3 * (size_t)n + 2];
     } else {
         // utils.py:300-352: i = x + 0.5, j = y + 0.5; dir = normalize([(i-cx)/fx, (j-cy)/fy, 1]) @ R^T
+        float P[12], fx = ri.fx, fy = ri.fy, cx = ri.cx, cy = ri.cy;
+        if (ri.dyn) {           // per-frame scalars from device memory (CUDA-graph replay): 16 broadcast loads
+            #pragma unroll
+            for (int k = 0; k < 12; k++) P[k] = __ldg(ri.dyn + k);
+            fx = __ldg(ri.dyn + 12); fy = __ldg(ri.dyn + 13); cx = __ldg(ri.dyn + 14); cy = __ldg(ri.dyn + 15);
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 12; k++) P[k] = ri.pose[k];
+        }
         const uint32_t py = n / ri.W, px = n - py * ri.W;
         const float i = __fadd_rn((float)px, 0.5f), j = __fadd_rn((float)py, 0.5f);
-        const float xs = __fdiv_rn(__fsub_rn(i, ri.cx), ri.fx);
-        const float ys = __fdiv_rn(__fsub_rn(j, ri.cy), ri.fy);
+        const float xs = __fdiv_rn(__fsub_rn(i, cx), fx);
+        const float ys = __fdiv_rn(__fsub_rn(j, cy), fy);
         const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(xs, xs), __fmul_rn(ys, ys)), 1.0f));
         const float ux = __fdiv_rn(xs, nrm), uy = __fdiv_rn(ys, nrm), uz = __fdiv_rn(1.0f, nrm);
-        dx = ri.pose[0] * ux + ri.pose[1] * uy + ri.pose[2] * uz;
-        dy = ri.pose[4] * ux + ri.pose[5] * uy + ri.pose[6] * uz;
-        dz = ri.pose[8] * ux + ri.pose[9] * uy + ri.pose[10] * uz;
-        ox = ri.pose[3]; oy = ri.pose[7]; oz = ri.pose[11];
+        dx = P[0] * ux + P[1] * uy + P[2] * uz;
+        dy = P[4] * ux + P[5] * uy + P[6] * uz;
+        dz = P[8] * ux + P[9] * uy + P[10] * uz;
+        ox = P[3]; oy = P[7]; oz = P[11];
     }
     st.rays_o[3 * (size_t)n] = ox; st.rays_o[3 * (size_t)n + 1] = oy; st.rays_o[3 * (size_t)n + 2] = oz;
     st.rays_d[3 * (size_t)n] = dx; st.rays_d[3 * (size_t)n + 1] = dy; st.rays_d[3 * (size_t)n + 2] = dz;
@@ -175,6 +187,7 @@ __global__ void k_rays_init(RayInit ri, RayState st) {
     st.wsum[n] = 0.f; st.depth[n] = 0.f;
     st.img[3 * (size_t)n] = 0.f; st.img[3 * (size_t)n + 1] = 0.f; st.img[3 * (size_t)n + 2] = 0.f;
     st.nsamp[n] = 0;
+    st.term[n] = 0;
     st.seg_cnt[n] = 0;
 }
 
@@ -291,6 +304,7 @@ __global__ void __launch_bounds__(128) k_composite_chunk(CompArgs a, RayState st
     if (dead) {
         st.alive[n] = 0;
         const uint32_t k = a.slots_before + (terminated ? step + 1 : cnt + 1);   // termination slot (1-based)
+        st.term[n] = (int)k;
         if (!a.budget_from_ctl && k <= a.max_steps) atomicAdd(ctl + CTL_HIST + k, 1u);
     } else {
         st.t[n] = t;
@@ -596,6 +610,7 @@ __global__ void k_finish(FinishArgs a, RayState st) {
     a.depth_map[n] = fmaxf(st.depth[n] - near, 0.f) / (far - near);
     if (a.weights_sum) a.weights_sum[n] = ws;
     if (a.n_samples) a.n_samples[n] = st.nsamp[n];
+    if (a.term_slot) a.term_slot[n] = st.term[n];
 }
 
 __global__ void k_hist_out(const uint32_t* __restrict__ ctl, uint32_t max_steps, uint32_t* __restrict__ out) {
@@ -649,6 +664,7 @@ static Workspace carve(void* base, uint32_t N) {
     w.st.img = (float*)take(sizeof(float) * 3 * N);
     w.st.alive = (uint8_t*)take(N);
     w.st.nsamp = (int*)take(sizeof(int) * N);
+    w.st.term = (int*)take(sizeof(int) * N);
     w.st.seg_off = (uint32_t*)take(sizeof(uint32_t) * N);
     w.st.seg_cnt = (uint32_t*)take(sizeof(uint32_t) * N);
     w.sb.pos4 = (float4*)take(sizeof(float4) * cap);
@@ -678,8 +694,10 @@ using namespace gf;
 #define ST(s) ((cudaStream_t)(s))
 
 namespace gf {
-int field_tc_launch(const GfModel* model, const FieldTcIO& io, cudaStream_t st);   // field_tc.cu
-int field_tc_kernel_count();                                                      // field_tc.cu
+int field_tc_launch(const GfModel* model, const FieldTcIO& io, cudaStream_t st);   // field_tc_split.cu
+int field_tc_kernel_count();
+int field_tc_pack(GfModel* m, cudaStream_t st);
+size_t field_tc_scratch_bytes(uint32_t M);
 }
 
 extern "C" {
@@ -796,7 +814,8 @@ GF_API int gf_model_create(const GfModelDesc* d, GfModel** out, gf_stream_t stre
         md.amb.lbase[l] = md.amb.table + lv_host[1].offset[l];
         md.torso.lbase[l] = md.torso.table ? md.torso.table + lv_host[2].offset[l] : nullptr;
     }
-    // tensor-core pack (field_tc.cu) is built lazily on first precision-1 use
+    // fp16 weight images of the tcgen05 pipeline (field_tc_split.cu): packed here, once -- the frame path never allocates or synchronises
+    if (int prc = field_tc_pack(m, st)) { cudaFree(w); delete m; return prc; }
     cudaFuncSetAttribute(k_field_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, FP32_SMEM_FLOATS * (int)sizeof(float));
     cudaFuncSetAttribute(k_torso_field, cudaFuncAttributeMaxDynamicSharedMemorySize, TORSO_SMEM_FLOATS * (int)sizeof(float));
     int dev = 0;
@@ -810,10 +829,7 @@ GF_API int gf_model_create(const GfModelDesc* d, GfModel** out, gf_stream_t stre
 GF_API void gf_model_destroy(GfModel* m) {
     if (!m) return;
     if (m->w) cudaFree(m->w);
-    if (m->tc_blob) cudaFree(m->tc_blob);
     if (m->tc2_blob) cudaFree(m->tc2_blob);
-    if (m->tc_scratch) cudaFree(m->tc_scratch);
-    if (m->scratch_bias) cudaFree(m->scratch_bias);
     for (int i = 0; i < GF_MAX_PROFILE_EVENTS; i++)
         if (m->ev[i]) cudaEventDestroy(m->ev[i]);
     delete m;
@@ -847,27 +863,33 @@ GF_API uint64_t gf_model_packed_bytes(const GfModel* m) { return m ? (uint64_t)m
 
 GF_API uint64_t gf_render_workspace_bytes(uint32_t N) { return (uint64_t)carve(nullptr, N).bytes; }
 
+GF_API uint64_t gf_field_workspace_bytes(uint32_t M, uint32_t precision) {
+    return 1024 + (precision ? (uint64_t)field_tc_scratch_bytes(M) : 0);
+}
+
 // Standalone field evaluation: the `self(xyzs, dirs, cond_feat, ind_code)` call of the reference loop
 // (renderer.py:342 -> radnerf.py:73-105).  xyzs/dirs [M,3]; sigmas [M]; rgbs [M,3]; ambient [M,2] or NULL.
-// scratch: device float[128] for the per-call cond bias.
+// workspace: caller-owned device scratch of gf_field_workspace_bytes(M, precision) bytes, 256-byte aligned (per-call cond bias +,
+// for precision 1, the hand-off buffers between the two tcgen05 kernels).  The model is not modified: re-entrant across streams.
 GF_API int gf_field_forward(const GfModel* model, const float* xyzs, const float* dirs, const float* cond_feat, uint32_t M, float* sigmas,
-                            float* rgbs, float* ambient, uint32_t precision, gf_stream_t stream) {
+                            float* rgbs, float* ambient, uint32_t precision, void* workspace, uint64_t workspace_bytes, gf_stream_t stream) {
     GF_REQUIRE(model && xyzs && dirs && cond_feat && sigmas && rgbs, "field_forward: null pointer");
+    GF_REQUIRE(precision <= 1, "field_forward: precision must be 0 (fp32) or 1 (fp16 tensor cores)");
     if (M == 0) return GF_OK;
+    GF_REQUIRE(workspace && ((uintptr_t)workspace & 255) == 0, "field_forward: workspace must be a 256-byte aligned device pointer");
+    GF_REQUIRE(workspace_bytes >= gf_field_workspace_bytes(M, precision), "field_forward: workspace too small (%llu < %llu)",
+               (unsigned long long)workspace_bytes, (unsigned long long)gf_field_workspace_bytes(M, precision));
     cudaStream_t st = ST(stream);
-    GfModel* mm = const_cast<GfModel*>(model);
-    if (!mm->scratch_bias) {
-        if (cudaMalloc(&mm->scratch_bias, sizeof(float) * 256) != cudaSuccess) { set_error("field_forward: cudaMalloc failed"); cudaGetLastError(); return GF_ERR_CUDA; }
-    }
+    float* bias = reinterpret_cast<float*>(workspace);
     FrameSetup fs;
     memset(&fs, 0, sizeof(fs));
     fs.cond_feat = cond_feat;
     fs.has_torso = 0;
-    k_frame_setup<<<1, 128, 0, st>>>(model->dev, fs, mm->scratch_bias, nullptr, nullptr);
+    k_frame_setup<<<1, 128, 0, st>>>(model->dev, fs, bias, nullptr, nullptr);
     if (precision == 0) {
         FieldIO io;
         memset(&io, 0, sizeof(io));
-        io.xyzs = xyzs; io.dirs = dirs; io.M_host = M; io.sigmas = sigmas; io.rgbs = rgbs; io.ambient = ambient; io.bias_amb = mm->scratch_bias;
+        io.xyzs = xyzs; io.dirs = dirs; io.M_host = M; io.sigmas = sigmas; io.rgbs = rgbs; io.ambient = ambient; io.bias_amb = bias;
         const uint32_t tiles = div_up(M, TILE_S);
         const uint32_t grid = tiles < (uint32_t)model->num_sms ? tiles : (uint32_t)model->num_sms;
         k_field_fp32<<<grid, DENSE_THREADS, FP32_SMEM_FLOATS * sizeof(float), st>>>(model->dev, io);
@@ -875,7 +897,10 @@ GF_API int gf_field_forward(const GfModel* model, const float* xyzs, const float
     }
     FieldTcIO io;
     memset(&io, 0, sizeof(io));
-    io.xyzs = xyzs; io.dirs = dirs; io.M_host = M; io.sigmas = sigmas; io.rgbs = rgbs; io.ambient = ambient; io.bias_amb = mm->scratch_bias;
+    io.xyzs = xyzs; io.dirs = dirs; io.M_host = M; io.sigmas = sigmas; io.rgbs = rgbs; io.ambient = ambient; io.bias_amb = bias;
+    char* scr = reinterpret_cast<char*>(workspace) + 1024;
+    io.feat_hi = reinterpret_cast<uint4*>(scr);
+    io.amb_pos = reinterpret_cast<float2*>(scr + (((size_t)M * 64 + 255) & ~size_t(255)));
     return field_tc_launch(model, io, st);
 }
 
@@ -909,6 +934,7 @@ GF_API int gf_render_frame(const GfModel* model, const GfFrame* f, const GfOut* 
     fs.cond_feat = f->cond_feat;
     memcpy(fs.torso_pose, f->torso_pose, sizeof(float) * 6);
     fs.has_torso = torso;
+    fs.dyn = f->dyn;
     k_frame_setup<<<torso ? 2 : 1, 128, 0, st>>>(model->dev, fs, w.bias_amb, w.bias_deform, w.bias_canon);
     launches++;
 
@@ -916,6 +942,7 @@ GF_API int gf_render_frame(const GfModel* model, const GfFrame* f, const GfOut* 
     memset(&ri, 0, sizeof(ri));
     ri.N = N; ri.W = f->W; ri.rays_o = f->rays_o; ri.rays_d = f->rays_d;
     memcpy(ri.pose, f->pose, sizeof(float) * 12);
+    ri.dyn = f->dyn;
     ri.fx = f->intrinsics[0]; ri.fy = f->intrinsics[1]; ri.cx = f->intrinsics[2]; ri.cy = f->intrinsics[3];
     memcpy(ri.aabb, d.aabb, sizeof(float) * 6);
     ri.min_near = d.min_near;
@@ -1004,7 +1031,7 @@ GF_API int gf_render_frame(const GfModel* model, const GfFrame* f, const GfOut* 
         fa.out_torso_alpha = o->torso_alpha_map; fa.out_torso_rgb = o->torso_rgb_map;
     }
     fa.N = N; fa.bg_color = f->bg_color; fa.rgb_map = o->rgb_map; fa.depth_map = o->depth_map; fa.weights_sum = o->weights_sum;
-    fa.n_samples = o->n_samples; fa.rgb8 = o->rgb8;
+    fa.n_samples = o->n_samples; fa.term_slot = o->term_slot; fa.rgb8 = o->rgb8;
     k_finish<<<div_up(N, 256), 256, 0, st>>>(fa, w.st);
     launches++;
     if (o->term_hist) k_hist_out<<<div_up(f->max_steps + 1, 256), 256, 0, st>>>(w.ctl, f->max_steps, o->term_hist);

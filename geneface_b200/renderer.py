@@ -52,14 +52,14 @@ class GfFrame(ctypes.Structure):
     _fields_ = [
         ("H", c_u32), ("W", c_u32), ("rays_o", c_vp), ("rays_d", c_vp), ("pose", c_f32 * 12), ("intrinsics", c_f32 * 4),
         ("cond_feat", c_vp), ("bg_color", c_vp), ("bg_coords", c_vp), ("torso_pose", c_f32 * 6), ("dt_gamma", c_f32),
-        ("max_steps", c_u32), ("T_thresh", c_f32), ("precision", c_u32),
+        ("max_steps", c_u32), ("T_thresh", c_f32), ("precision", c_u32), ("dyn", c_vp),
     ]
 
 
 class GfOut(ctypes.Structure):
     _fields_ = [
         ("rgb_map", c_vp), ("depth_map", c_vp), ("weights_sum", c_vp), ("torso_alpha_map", c_vp), ("torso_rgb_map", c_vp),
-        ("n_samples", c_vp), ("rgb8", c_vp), ("counters", c_vp), ("term_hist", c_vp),
+        ("n_samples", c_vp), ("rgb8", c_vp), ("counters", c_vp), ("term_hist", c_vp), ("term_slot", c_vp),
     ]
 
 
@@ -191,7 +191,7 @@ class NeRFRenderer(nn.Module):
         if steps > 0:
             self.mean_count = int(self.step_counter[:steps, 0].sum().item() / steps)
         self.local_step = 0
-        self._gf_key = None   # bitfield changed -> rebuild fused model lazily
+        self.invalidate_fused()   # bitfield changed -> rebuild fused model lazily
 
     # -- fused path plumbing ----------------------------------------------------------------------------------
     def _fused_supported(self):
@@ -200,9 +200,34 @@ class NeRFRenderer(nn.Module):
     def _tensors_key(self):
         return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
 
-    def gf_model(self):
-        """Build (or reuse) the packed GfModel for the current weights."""
+    def invalidate_fused(self):
+        """Drop the packed GfModel (and every captured frame graph): the next fused call re-packs from the live tensors.
+        Called automatically by load_state_dict / train() / eval() / _apply (.to, .cuda, .half) and by the grid-maintenance
+        routines; call it yourself after in-place edits that bypass autograd's version counter (`p.data.copy_`, EMA weight
+        surgery, optimizers writing through .data)."""
+        self._gf_key = None
+        self._gf_epoch = getattr(self, '_gf_epoch', 0) + 1
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.invalidate_fused()
+        return r
+
+    def train(self, mode=True):
+        self.invalidate_fused()
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_fused()
+        return super()._apply(fn, *a, **k)
+
+    def gf_model(self, check=True):
+        """Build (or reuse) the packed GfModel for the current weights.  check=True walks every parameter / buffer
+        (data_ptr, version) to detect in-place updates (~0.2 ms of host time); the sequence / graph paths pass check=False
+        and rely on invalidate_fused()."""
         _lib.require_cuda()
+        if self._gf_model is not None and self._gf_key is not None and not check:
+            return self._gf_model
         key = self._tensors_key()
         if self._gf_model is not None and key == self._gf_key:
             return self._gf_model
@@ -212,6 +237,7 @@ class NeRFRenderer(nn.Module):
         check(_lib.lib().gf_model_create(ctypes.byref(desc), ctypes.byref(handle), stream_ptr()), "gf_model_create")
         torch.cuda.current_stream().synchronize()
         self._gf_model, self._gf_key, self._gf_keep = handle, key, keep
+        self._gf_epoch = getattr(self, '_gf_epoch', 0) + 1          # captured frame graphs hold the old handle: they re-capture
         return handle
 
     def free_gf_model(self):
@@ -241,14 +267,19 @@ class NeRFRenderer(nn.Module):
         amb = torch.empty(M, 2, dtype=torch.float32, device=xyzs.device)
         cf = cond_feat.float().contiguous().view(-1)
         prec = PRECISIONS[precision or self.precision]
-        check(_lib.lib().gf_field_forward(model, ptr(xyzs), ptr(dirs), ptr(cf), M, ptr(sig), ptr(rgb), ptr(amb), prec, stream_ptr()),
-              "gf_field_forward")
+        need = _lib.lib().gf_field_workspace_bytes(M, prec)
+        ws = torch.empty(need, dtype=torch.uint8, device=xyzs.device)          # caller-owned scratch (the library never allocates)
+        check(_lib.lib().gf_field_forward(model, ptr(xyzs), ptr(dirs), ptr(cf), M, ptr(sig), ptr(rgb), ptr(amb), prec, ptr(ws), need,
+                                          stream_ptr()), "gf_field_forward")
         return sig, rgb, amb
 
     def render_fused(self, cond_feat, H, W, *, rays_o=None, rays_d=None, pose=None, intrinsics=None, bg_color=None, bg_coords=None,
-                     torso_pose=None, dt_gamma=0.0, max_steps=1024, T_thresh=1e-4, precision=None, want=('weights_sum',), out=None):
-        """One `gf_render_frame` call.  Either rays_o/rays_d [N,3] or pose [3|4,4] + intrinsics.  Returns dict of tensors."""
-        model = self.gf_model()
+                     torso_pose=None, dt_gamma=0.0, max_steps=1024, T_thresh=1e-4, precision=None, want=('weights_sum',), out=None,
+                     dyn=None, check_weights=True):
+        """One `gf_render_frame` call.  Rays come from rays_o/rays_d [N,3], or from pose [3|4,4] + intrinsics (by value), or from
+        `dyn` = DEVICE float[22] (pose[12] | intrinsics[4] | torso_pose[6]) read at execution time -- the CUDA-graph form: no host
+        conversion, nothing frame-specific in the launch arguments.  Returns dict of tensors."""
+        model = self.gf_model(check=check_weights)
         dev = cond_feat.device
         N = H * W
         fr = GfFrame()
@@ -258,6 +289,9 @@ class NeRFRenderer(nn.Module):
             rays_d = rays_d.float().contiguous().view(-1, 3)
             assert rays_o.shape[0] == N
             fr.rays_o, fr.rays_d = rays_o.data_ptr(), rays_d.data_ptr()
+        elif dyn is not None:
+            assert dyn.is_cuda and dyn.dtype == torch.float32 and dyn.numel() == 22 and dyn.is_contiguous()
+            fr.dyn = dyn.data_ptr()
         else:
             p = np.asarray(pose.detach().cpu() if torch.is_tensor(pose) else pose, dtype=np.float32).reshape(-1, 4)[:3]
             fr.pose = (c_f32 * 12)(*p.reshape(-1).tolist())
@@ -273,7 +307,7 @@ class NeRFRenderer(nn.Module):
         if bg_coords is not None:
             bg_coords = bg_coords.float().contiguous().view(-1, 2)
             fr.bg_coords = bg_coords.data_ptr()
-        if torso_pose is not None:
+        if torso_pose is not None and dyn is None:
             tp = torso_pose.detach().float().cpu().view(-1).tolist() if torch.is_tensor(torso_pose) else list(torso_pose)
             fr.torso_pose = (c_f32 * 6)(*tp)
         fr.dt_gamma, fr.max_steps, fr.T_thresh = float(dt_gamma), int(max_steps), float(T_thresh)
@@ -287,7 +321,7 @@ class NeRFRenderer(nn.Module):
         o.rgb_map, o.depth_map = res['rgb_map'].data_ptr(), res['depth_map'].data_ptr()
         shapes = {'weights_sum': ((N,), torch.float32), 'torso_alpha_map': ((N,), torch.float32), 'torso_rgb_map': ((N, 3), torch.float32),
                   'n_samples': ((N,), torch.int32), 'rgb8': ((N, 3), torch.uint8), 'counters': ((4,), torch.int64),
-                  'term_hist': ((int(max_steps) + 1,), torch.int32)}
+                  'term_hist': ((int(max_steps) + 1,), torch.int32), 'term_slot': ((N,), torch.int32)}
         for name in want:
             if name not in res:
                 shp, dt = shapes[name]
@@ -296,7 +330,7 @@ class NeRFRenderer(nn.Module):
         ws, need = self._workspace(N, dev)
         check(_lib.lib().gf_render_frame(model, ctypes.byref(fr), ctypes.byref(o), ptr(ws), need, stream_ptr()), "gf_render_frame")
         # keep temporaries alive until the stream has consumed them
-        res['_keep'] = (rays_o, rays_d, cf, bg_color, bg_coords)
+        res['_keep'] = (rays_o, rays_d, cf, bg_color, bg_coords, dyn)
         return res
 
     # -- the reference boundary ------------------------------------------------------------------------------------
@@ -350,12 +384,13 @@ class NeRFRenderer(nn.Module):
         if not use_loop:
             out = self.render_fused(cond_feat.detach(), 1, N, rays_o=rays_o, rays_d=rays_d, bg_color=bg_color, dt_gamma=dt_gamma,
                                     max_steps=max_steps, T_thresh=T_thresh, precision=kwargs.get('precision'),
-                                    want=('weights_sum', 'n_samples', 'counters', 'term_hist'))
+                                    want=('weights_sum', 'n_samples', 'counters', 'term_hist', 'term_slot'))
             results['depth_map'] = out['depth_map'].view(*prefix)
             results['rgb_map'] = out['rgb_map'].view(*prefix, 3)
             results['weights_sum_eval'] = out['weights_sum']
             results['n_samples'] = out['n_samples']
             results['term_hist'] = out['term_hist']
+            results['term_slot'] = out['term_slot']
             self.last_counters = out['counters']
             return results
         nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer, self.min_near)
@@ -581,7 +616,7 @@ class RADNeRFTorso(RADNeRF):
             out = self.render_fused(cond_feat, 1, N, rays_o=rays_o, rays_d=rays_d, bg_color=bg_color, bg_coords=bg_coords,
                                     torso_pose=poses, dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh,
                                     precision=kwargs.get('precision'),
-                                    want=('weights_sum', 'torso_alpha_map', 'torso_rgb_map', 'n_samples', 'counters', 'term_hist'))
+                                    want=('weights_sum', 'torso_alpha_map', 'torso_rgb_map', 'n_samples', 'counters', 'term_hist', 'term_slot'))
             results['torso_alpha_map'] = out['torso_alpha_map'].view(N, 1)
             results['torso_rgb_map'] = out['torso_rgb_map'].view(1, N, 3) if len(prefix) == 2 else out['torso_rgb_map']
             results['depth_map'] = out['depth_map'].view(*prefix)
@@ -589,6 +624,7 @@ class RADNeRFTorso(RADNeRF):
             results['weights_sum_eval'] = out['weights_sum']
             results['n_samples'] = out['n_samples']
             results['term_hist'] = out['term_hist']
+            results['term_slot'] = out['term_slot']
             self.last_counters = out['counters']
             return results
         # ---- reference structure (radnerf_torso.py:92-196) on our ops ----
@@ -658,4 +694,4 @@ class RADNeRFTorso(RADNeRF):
         fresh = F.max_pool2d(fresh.view(1, 1, G, G), kernel_size=5, stride=1, padding=2).view(-1)
         self.density_grid_torso = torch.maximum(self.density_grid_torso * decay, fresh)
         self.mean_density_torso = torch.mean(self.density_grid_torso).item()
-        self._gf_key = None
+        self.invalidate_fused()

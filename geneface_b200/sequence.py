@@ -37,16 +37,105 @@ def broadcast_model_(model, src=0):
     dist.broadcast(extra, src=src)
     if hasattr(model, 'mean_density_torso'):
         model.mean_density_torso = float(extra.item())
-    model._gf_key = None
+    model.invalidate_fused()
     return total
 
 
-class SequenceRenderer:
-    """Renders frames [start, end) of a (pose, cond) sequence on this rank's GPU into a pinned host ring."""
+DYN_FLOATS = 22          # pose[12] | intrinsics[4] | torso_pose[6]   (GfFrame.dyn, include/gfrender.h)
 
-    def __init__(self, model, H, W, intrinsics, precision='fp16', max_steps=16, dt_gamma=1 / 256, torso=True):
+
+def pack_frame_inputs(poses, conds, intrinsics, torso=True):
+    """Host-side packing of a whole sequence into ONE pinned array [F, C + 22] (float32): per frame the flattened condition window
+    (smo_win * cond_win * cond_dim floats) followed by the 22 per-frame scalars the kernels read from device memory (c2w rows 0..2,
+    intrinsics, convert_poses(pose)).  One H2D copy of a row is everything a frame needs."""
+    from .utils import convert_poses
+    F = poses.shape[0]
+    poses = torch.as_tensor(poses, dtype=torch.float32).cpu()
+    conds = conds.float().cpu().reshape(F, -1)
+    C = conds.shape[1]
+    packed = torch.empty(F, C + DYN_FLOATS, dtype=torch.float32)
+    if torch.cuda.is_available():
+        packed = packed.pin_memory()
+    packed[:, :C] = conds
+    packed[:, C:C + 12] = poses[:, :3, :4].reshape(F, 12)
+    packed[:, C + 12:C + 16] = torch.tensor([float(v) for v in intrinsics])
+    packed[:, C + 16:] = convert_poses(poses) if torso else 0.0
+    return packed
+
+
+class FrameGraph:
+    """One captured CUDA graph of {condition encoder -> gf_render_frame -> RGB8} for a fixed (model, H, W, settings, background,
+    output buffer).  Per frame the host rewrites `self.inputs` (device float[C + 22], normally by one async H2D copy of a
+    pack_frame_inputs row) and calls replay(): a single graph launch instead of ~20 torch + ~25 libgfrender launches."""
+
+    def __init__(self, model, H, W, cond_shape, bg_color, out_rgb8, *, precision='fp16', max_steps=16, dt_gamma=1 / 256, torso=True,
+                 want=('rgb8',), extra_out=None):
+        self.model, self.H, self.W = model, H, W
+        self.cond_shape = tuple(cond_shape)
+        dev = out_rgb8.device
+        C = 1
+        for d in self.cond_shape:
+            C *= d
+        self.C = C
+        self.inputs = torch.zeros(C + DYN_FLOATS, dtype=torch.float32, device=dev)
+        self.out = dict(extra_out or {})
+        self.out['rgb8'] = out_rgb8
+        self.bg_color = bg_color
+        self.kw = dict(bg_color=bg_color, dt_gamma=dt_gamma, max_steps=max_steps, precision=precision, want=tuple(want))
+        self.epoch = None
+        self.graph = None
+
+    def _frame(self):
+        cond = self.inputs[:self.C].view(self.cond_shape)
+        cf = self.model.cal_cond_feat(cond)
+        self.model.render_fused(cf, self.H, self.W, dyn=self.inputs[self.C:], out=self.out, check_weights=False, **self.kw)
+
+    @torch.no_grad()
+    def capture(self):
+        self.model.gf_model()                        # pack (or re-pack) the weights outside the capture
+        self.epoch = self.model._gf_epoch
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):                   # warm-up on a side stream: cuDNN / cuBLAS handles, lazy module state
+            for _ in range(2):
+                self._frame()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._frame()
+
+    def replay(self):
+        if self.graph is None or self.epoch != self.model._gf_epoch:     # weights were re-packed: the old graph holds a dead handle
+            self.capture()
+        self.graph.replay()
+
+
+class SequenceRenderer:
+    """Renders frames [start, end) of a (pose, cond) sequence on this rank's GPU into a pinned host ring.
+
+    graph=True (default): every frame is one H2D copy of its packed inputs (condition window + 22 scalars), one CUDA-graph replay
+    and one D2H copy of the RGB8 frame on a copy stream -- the host does no per-frame tensor work.  graph=False keeps the eager
+    per-frame path (cond encoder modules + ~25 launches through render_fused)."""
+
+    def __init__(self, model, H, W, intrinsics, precision='fp16', max_steps=16, dt_gamma=1 / 256, torso=True, graph=True):
         self.model, self.H, self.W, self.intrinsics = model, H, W, intrinsics
         self.precision, self.max_steps, self.dt_gamma, self.torso = precision, max_steps, dt_gamma, torso
+        self.graph = graph
+        # device-side RGB8 double buffer and the copy stream live as long as the renderer (allocated once, not per render() call)
+        self.device = next(model.parameters()).device
+        self._dev_rgb8 = [torch.empty(H * W, 3, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self._copy_stream = torch.cuda.Stream()
+        self._graphs = [None, None]
+        self._graph_key = None
+
+    def _frame_graphs(self, cond_shape, bg_color):
+        key = (tuple(cond_shape), None if bg_color is None else bg_color.data_ptr())
+        if self._graph_key != key:
+            self._graphs = [FrameGraph(self.model, self.H, self.W, cond_shape, bg_color, self._dev_rgb8[i], precision=self.precision,
+                                       max_steps=self.max_steps, dt_gamma=self.dt_gamma, torso=self.torso) for i in range(2)]
+            self._graph_key = key
+        return self._graphs
 
     @torch.no_grad()
     def render(self, poses, conds, bg_color, start, end, out_rgb8=None, sink=None):
@@ -57,9 +146,7 @@ class SequenceRenderer:
         n = end - start
         N = self.H * self.W
         host = out_rgb8 if out_rgb8 is not None else torch.empty(n, self.H, self.W, 3, dtype=torch.uint8).pin_memory()
-        dev = next(self.model.parameters()).device
-        dev_rgb8 = [torch.empty(N, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
-        copy_stream = torch.cuda.Stream()
+        dev_rgb8, copy_stream = self._dev_rgb8, self._copy_stream
         done = [None, None]
         landed, flushed = [], 0                    # per-frame "in host memory" events; frames already handed to the sink
 
@@ -70,18 +157,26 @@ class SequenceRenderer:
                 sink(start + flushed, host[flushed].numpy())
                 flushed += 1
 
+        use_graph = self.graph and not conds.is_cuda
+        if use_graph:
+            packed = pack_frame_inputs(poses[start:end], conds[start:end], self.intrinsics, self.torso)
+            graphs = self._frame_graphs(conds.shape[1:], bg_color)
         for k, f in enumerate(range(start, end)):
             slot = k & 1
             if done[slot] is not None:
                 torch.cuda.current_stream().wait_event(done[slot])
-            cond_f = conds[f]
-            if not cond_f.is_cuda:
-                cond_f = cond_f.to(dev_rgb8[0].device, non_blocking=True)
-            cond_feat = self.model.cal_cond_feat(cond_f)
-            pose6 = convert_poses(poses[f:f + 1]) if self.torso else None
-            self.model.render_fused(cond_feat, self.H, self.W, pose=poses[f], intrinsics=self.intrinsics, bg_color=bg_color, torso_pose=pose6,
-                                    dt_gamma=self.dt_gamma, max_steps=self.max_steps, precision=self.precision, want=('rgb8',),
-                                    out={'rgb8': dev_rgb8[slot]})
+            if use_graph:
+                graphs[slot].inputs.copy_(packed[k], non_blocking=True)
+                graphs[slot].replay()
+            else:
+                cond_f = conds[f]
+                if not cond_f.is_cuda:
+                    cond_f = cond_f.to(dev_rgb8[0].device, non_blocking=True)
+                cond_feat = self.model.cal_cond_feat(cond_f)
+                pose6 = convert_poses(poses[f:f + 1]) if self.torso else None
+                self.model.render_fused(cond_feat, self.H, self.W, pose=poses[f], intrinsics=self.intrinsics, bg_color=bg_color, torso_pose=pose6,
+                                        dt_gamma=self.dt_gamma, max_steps=self.max_steps, precision=self.precision, want=('rgb8',),
+                                        out={'rgb8': dev_rgb8[slot]})
             ev = torch.cuda.Event()
             ev.record()
             with torch.cuda.stream(copy_stream):

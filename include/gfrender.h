@@ -224,6 +224,10 @@ typedef struct GfFrame {
     uint32_t max_steps;          /* render(max_steps=...) */
     float T_thresh;              /* 1e-4 default */
     uint32_t precision;          /* 0 = fp32 SIMT (reference arithmetic), 1 = fp16 tensor cores (tcgen05) */
+    const float* dyn;            /* NULL, or DEVICE float[22] = pose[12] | intrinsics[4] | torso_pose[6]: the per-frame scalars are then
+                                    read from device memory at execution time instead of travelling by value in the launch, so that
+                                    ONE captured CUDA graph of gf_render_frame replays for every frame of a sequence (the host
+                                    only rewrites these 88 bytes and cond_feat's source) */
 } GfFrame;
 
 typedef struct GfOut {
@@ -238,12 +242,18 @@ typedef struct GfOut {
     uint32_t* term_hist;         /* device uint32[max_steps+1] or NULL: term_hist[k] = number of rays whose termination
                                     slot is k (1..max_steps); replaying renderer.py:326-351 over it yields the reference
                                     host loop's (n_alive, n_step) sequence.  term_hist[0] = S_total. */
+    int32_t* term_slot;          /* [N] or NULL: per-ray termination slot (1-based: T < T_thresh at sample j -> j; ran dry after m
+                                    samples -> m+1; missed the aabb -> 1), 0 for a ray still alive after the last round.  The
+                                    reference marks the ray dead (rays_alive = -1, raymarching.cu:1017) in the host-loop
+                                    iteration whose offered slots contain it; a slot > S_total was never observed by that loop. */
 } GfOut;
 
 /* Standalone field evaluation = the `self(xyzs, dirs, cond_feat, ind_code)` call inside the reference
  * loop (renderer.py:342 -> radnerf.py:73-105).  xyzs, dirs [M,3]; sigmas [M]; rgbs [M,3]; ambient [M,2] or NULL. */
+GF_API uint64_t gf_field_workspace_bytes(uint32_t M, uint32_t precision);
 GF_API int gf_field_forward(const GfModel* model, const float* xyzs, const float* dirs, const float* cond_feat, uint32_t M,
-                            float* sigmas, float* rgbs, float* ambient, uint32_t precision, gf_stream_t stream);
+                            float* sigmas, float* rgbs, float* ambient, uint32_t precision, void* workspace,
+                            uint64_t workspace_bytes, gf_stream_t stream);
 
 /* Profiling: when enabled, gf_render_frame brackets every field-kernel launch with CUDA events on the launching
  * stream; after synchronising, gf_profile_field_ms returns their summed duration for the last frame. */

@@ -8,6 +8,12 @@ sources where they lie under /root/reference (never copied into this repo):
     modules/radnerfs/encoders/shencoder/src/{shencoder.cu,bindings.cpp}   -> _shencoder
     modules/radnerfs/encoders/freqencoder/src/{freqencoder.cu,bindings.cpp} -> _freqencoder
 
+Beside them, the UNMODIFIED reference Python of the path (PY_FILES below: renderer / radnerf / radnerf_torso /
+cond_encoder / utils, the raymarching + encoder Function wrappers and utils/commons/hparams) is mirrored, byte for byte
+and at build time only, into oracle/_ref/pyref/ so that the reference's own `RADNeRFTorso.render()` can run on the GPU
+box where /root/reference does not exist (oracle/ref_model.py imports it from there).  oracle/_ref/ is git-ignored:
+no reference source enters the repository history.
+
 The only deviation from the reference's own JIT recipe (raymarching/backend.py:6-12)
 is -std=c++17 instead of c++14 (torch 2.11 headers need C++17) and the explicit
 sm_100a arch.  Outputs go to oracle/_ref/<name>/<name>.so (git-ignored, shipped
@@ -34,6 +40,33 @@ CU = {
     "_shencoder": "shencoder.cu",
     "_freqencoder": "freqencoder.cu",
 }
+
+
+# reference Python mirrored (unmodified) into oracle/_ref/pyref/, relative to the reference root
+PY_FILES = [
+    "modules/radnerfs/renderer.py", "modules/radnerfs/radnerf.py", "modules/radnerfs/radnerf_torso.py",
+    "modules/radnerfs/cond_encoder.py", "modules/radnerfs/utils.py",
+    "modules/radnerfs/raymarching/__init__.py", "modules/radnerfs/raymarching/raymarching.py", "modules/radnerfs/raymarching/backend.py",
+    "modules/radnerfs/encoders/encoding.py",
+    "modules/radnerfs/encoders/gridencoder/__init__.py", "modules/radnerfs/encoders/gridencoder/grid.py", "modules/radnerfs/encoders/gridencoder/backend.py",
+    "modules/radnerfs/encoders/shencoder/__init__.py", "modules/radnerfs/encoders/shencoder/sphere_harmonics.py", "modules/radnerfs/encoders/shencoder/backend.py",
+    "modules/radnerfs/encoders/freqencoder/__init__.py", "modules/radnerfs/encoders/freqencoder/freq.py", "modules/radnerfs/encoders/freqencoder/backend.py",
+    "utils/commons/hparams.py", "utils/commons/os_utils.py",
+]
+
+
+def mirror_python():
+    """Byte-for-byte mirror of PY_FILES into oracle/_ref/pyref (namespace packages, like the reference tree)."""
+    dst_root = os.path.join(OUT, "pyref")
+    n = 0
+    for rel in PY_FILES:
+        src = os.path.join(REF, rel)
+        dst = os.path.join(dst_root, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if not os.path.exists(dst) or open(src, "rb").read() != open(dst, "rb").read():
+            shutil.copyfile(src, dst)
+            n += 1
+    print("[oracle/_ref] pyref: %d files mirrored (%d refreshed)" % (len(PY_FILES), n))
 
 
 def built(name):
@@ -64,6 +97,7 @@ def main():
         print("reference tree not present (%s): skipping oracle/_ref build" % REF)
         return 0
     os.makedirs(OUT, exist_ok=True)
+    mirror_python()
     names = sys.argv[1:] or list(EXTS)
     for n in names:
         if built(n):

@@ -195,8 +195,10 @@ def convert_poses(pose):
 
 # ------------------------------------------------------------------ head render loop
 def render_head(field, sd, rays_o, rays_d, cond_feat, bitfield, cascade, grid_size, aabb, min_near,
-                dt_gamma, max_steps, T_thresh=1e-4, trace=None):
-    """renderer.py:314-351 (eval branch).  Returns weights_sum, depth, image, nears, fars, n_samples[N]."""
+                dt_gamma, max_steps, T_thresh=1e-4, trace=None, term_iter=None):
+    """renderer.py:314-351 (eval branch).  Returns weights_sum, depth, image, nears, fars, n_samples[N].
+    term_iter: optional int32[N] (pre-filled with -1) receiving the loop iteration in which composite_rays marked the ray dead
+    (rays_alive[n] = -1, raymarching.cu:1017)."""
     N = rays_o.shape[0]
     nears, fars = ops.near_far_from_aabb(rays_o, rays_d, aabb, min_near)
     ind_code = _sd(sd, 'individual_embeddings')[0] if 'individual_embeddings' in sd else None
@@ -220,6 +222,8 @@ def render_head(field, sd, rays_o, rays_d, cond_feat, bitfield, cascade, grid_si
         ids = rays_alive.copy()
         composited = ops.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh)
         n_samples[ids] += composited
+        if term_iter is not None:
+            term_iter[ids[rays_alive < 0]] = len(trace) - 1 if trace is not None else -2
         rays_alive = np.ascontiguousarray(rays_alive[rays_alive >= 0])
         step += n_step
     return weights_sum, depth, image, nears, fars, n_samples

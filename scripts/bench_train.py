@@ -20,10 +20,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     args = ap.parse_args()
+    print(json.dumps(run(args.steps, args.warmup, 0, args.rays)), flush=True)
+
+
+def run(steps=20, warmup=5, local=0, rays=4096):
+    args = argparse.Namespace(steps=steps, warmup=warmup, rays=rays)
     import torch
     from geneface_b200 import synthetic, utils
     assert torch.cuda.is_available(), "needs a GPU"
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", local)
     H = W = 512
     model, hp = synthetic.build_model(torso=False, bitfield='S', seed=0, device=dev)
     model.train()
@@ -68,7 +73,7 @@ def main():
     line = {"metric": "train step, %d rays (march_rays_train + field + composite + backward + Adam)" % args.rays, "ms_per_step": ms,
             "rays_per_s": args.rays / (ms / 1000.0), "loss": float(loss), "grads_finite": bool(all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)),
             "top_kernels": [{"name": r.key[:70], "share": r.device_time_total / tot, "calls": r.count} for r in rows]}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 if __name__ == "__main__":

@@ -65,12 +65,26 @@ def test_argument_validation_happens_before_any_launch():
     assert L.gf_render_workspace_bytes(512 * 512) > 512 * 512 * 32 * 40
 
 
-def test_ctypes_structs_match_the_header_layout():
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every field of the three ABI structs, computed by gcc FROM include/gfrender.h, against the ctypes mirrors."""
+    import subprocess
     from geneface_b200.renderer import GfFrame, GfModelDesc, GfOut
-    # sizes computed from the C declarations with natural alignment (x86-64): catches field drift
-    assert ctypes.sizeof(GfOut) == 9 * 8
-    assert ctypes.sizeof(GfFrame) == 8 + 16 + 48 + 16 + 24 + 24 + 4 + 4 + 4 + 4
-    assert ctypes.sizeof(GfModelDesc) % 8 == 0 and GfModelDesc.density_bitfield.offset % 8 == 0
+    structs = {"GfOut": GfOut, "GfFrame": GfFrame, "GfModelDesc": GfModelDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gfrender.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{fname} %zu\\n", offsetof({name}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == ctypes.sizeof(cls), f"sizeof({name}): header {got[name]} vs ctypes {ctypes.sizeof(cls)}"
+        for fname, _ in cls._fields_:
+            assert int(got[f"{name}.{fname}"]) == getattr(cls, fname).offset, f"offsetof({name}, {fname})"
 
 
 def test_no_product_module_imports_the_oracle():

@@ -240,7 +240,7 @@ def test_sequence_renderer_pipeline_logic_with_a_fake_device(monkeypatch):
     poses[:, 0, 3] = torch.arange(F).float() + 10
     conds = torch.randn(F, 5, 1, 204)
     host = torch.zeros(F - 2, H, W, 3, dtype=torch.uint8)
-    seq = sequence.SequenceRenderer(FakeModel(), H, W, (1.0, 1.0, 2.0, 2.0), torso=False)
+    seq = sequence.SequenceRenderer(FakeModel(), H, W, (1.0, 1.0, 2.0, 2.0), torso=False, graph=False)      # eager per-frame path
     sunk = []
     out = seq.render(poses, conds, None, 2, F, out_rgb8=host, sink=lambda idx, fr: sunk.append((idx, int(fr[0, 0, 0]))))
     assert out is host
@@ -251,3 +251,21 @@ def test_sequence_renderer_pipeline_logic_with_a_fake_device(monkeypatch):
     log.clear()
     seq.render(poses, conds, None, 0, 3, out_rgb8=torch.zeros(3, H, W, 3, dtype=torch.uint8))
     assert log == []
+
+
+def test_packed_frame_inputs_layout():
+    """sequence.pack_frame_inputs: one row per frame = flattened condition window | c2w rows 0..2 | fx fy cx cy | convert_poses(pose)
+    -- exactly the 22 floats GfFrame.dyn documents (include/gfrender.h), so that one H2D copy feeds a graph replay."""
+    from geneface_b200 import sequence, utils
+    F = 3
+    poses = torch.stack([torch.from_numpy(utils.orbit_pose(3.35, 7.0 * f)) for f in range(F)])
+    conds = torch.randn(F, 5, 1, 204, generator=torch.Generator().manual_seed(0))
+    intr = (1365.3, 1365.3, 256.0, 256.0)
+    p = sequence.pack_frame_inputs(poses, conds, intr, torso=True)
+    assert p.shape == (F, 1020 + sequence.DYN_FLOATS) and p.dtype == torch.float32
+    for f in range(F):
+        assert torch.equal(p[f, :1020], conds[f].reshape(-1))
+        assert torch.equal(p[f, 1020:1032], poses[f, :3, :4].reshape(-1).float())
+        assert torch.allclose(p[f, 1032:1036], torch.tensor(intr))
+        assert torch.equal(p[f, 1036:], utils.convert_poses(poses[f:f + 1])[0])
+    assert torch.count_nonzero(sequence.pack_frame_inputs(poses, conds, intr, torso=False)[:, 1036:]) == 0
