@@ -120,6 +120,7 @@ _SIGS = {
     "gf_adnerf_embed_points": [c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_vp, c_u32, c_vp],
     "gf_adnerf_raw2outputs": [c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "gf_adnerf_sample_pdf": [c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_int, c_vp, c_vp, c_vp],
+    "gf_get_rays": [c_vp, c_u32, c_f32, c_f32, c_f32, c_f32, c_u32, c_u32, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp],
     "gf_model_create": [c_vp, c_vp, c_vp],
     "gf_model_destroy": [c_vp],
     "gf_model_packed_bytes": [c_vp],

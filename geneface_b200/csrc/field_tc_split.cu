@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                     if (a.io.pos4) {
                         const int ray = __float_as_int(a.io.pos4[i].w);
                         r.dir.x = __ldg(a.io.rays_d + 3 * (size_t)ray); r.dir.y = __ldg(a.io.rays_d + 3 * (size_t)ray + 1); r.dir.z = __ldg(a.io.rays_d + 3 * (size_t)ray + 2);
-                    } else { r.dir.x = a.io.dirs[3 * (size_t)i]; r.dir.y = a.io.dirs[3 * (size_t)i + 1]; r.dir.z = a.io.dirs[3 * (size_t)i + 2]; }
+                    } else if (a.io.dirs) { r.dir.x = a.io.dirs[3 * (size_t)i]; r.dir.y = a.io.dirs[3 * (size_t)i + 1]; r.dir.z = a.io.dirs[3 * (size_t)i + 2]; }
                 }
             }
             return r;
@@ -506,6 +506,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
         const uint32_t bar_mma = sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT + stream);
         const uint32_t w_addr = sbase;
         const bool leader = row == 0;
+        const bool sigma_only = !a.io.out4 && !a.io.rgbs;          // density query (uniform)
         uint32_t phase = 0;
         for (uint32_t j = stream; j < my_tiles; j += 2) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
@@ -554,6 +555,26 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 4 * 128 * 144 : nullptr);
             tc_fence_before();
             bar_named(1 + stream, 128);
+            if (sigma_only) {
+                // density query: only the sigma-logit row block of the merged layer (rows 128..143 of the image, N = 16); no colour net
+                if (leader) {
+                    tc_fence_after();
+                    #pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_MRG + (k >> 2) * (144 * 128) + 128 * 128 + 32 * (k & 3)), idesc_f16(16), k);
+                    mma_commit(bar_mma);
+                }
+                stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
+                tc_fence_after();
+                if (leader) mbar_arrive(bar_empty + 8 * slot);
+                float s4[4];
+                tmem_ld4(t_d, s4);
+                if (valid) {
+                    a.io.sigmas[i] = __expf(s4[0]);
+                    if (a.io.ambient) { const float2 ap = a.io.amb_pos[i]; a.io.ambient[2 * (size_t)i] = ap.x; a.io.ambient[2 * (size_t)i + 1] = ap.y; }
+                }
+                continue;
+            }
             // ---- merged sigma layer 2 x colour layer 0 (N = 144) + SH part (SS, K = 16, N = 128) --------------------------
             if (leader) {
                 tc_fence_after();

@@ -146,6 +146,41 @@ __global__ void k_frame_setup(ModelDev m, FrameSetup fs, float* __restrict__ bia
 // ======================================================================================
 // Tile-friendly ray order is NOT applied here: ray n is pixel (y = n / W, x = n % W), the
 // reference's order (utils.py:301-303).
+// utils.py:300-352: i = x + 0.5, j = y + 0.5; dir = normalize([(i-cx)/fx, (j-cy)/fy, 1]) @ R^T; origin = translation.  P = c2w rows 0..2.
+__device__ __forceinline__ void pixel_ray(const float (&P)[12], float fx, float fy, float cx, float cy, uint32_t px, uint32_t py,
+                                          float& ox, float& oy, float& oz, float& dx, float& dy, float& dz, float& i, float& j) {
+    i = __fadd_rn((float)px, 0.5f); j = __fadd_rn((float)py, 0.5f);
+    const float xs = __fdiv_rn(__fsub_rn(i, cx), fx);
+    const float ys = __fdiv_rn(__fsub_rn(j, cy), fy);
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(xs, xs), __fmul_rn(ys, ys)), 1.0f));
+    const float ux = __fdiv_rn(xs, nrm), uy = __fdiv_rn(ys, nrm), uz = __fdiv_rn(1.0f, nrm);
+    dx = P[0] * ux + P[1] * uy + P[2] * uz;
+    dy = P[4] * ux + P[5] * uy + P[6] * uz;
+    dz = P[8] * ux + P[9] * uy + P[10] * uz;
+    ox = P[3]; oy = P[7]; oz = P[11];
+}
+
+// get_rays as a fine-grained op (utils.py:282-363): rays for a list of flat pixel indices (inds == null: all H*W pixels in order) of B poses
+__global__ void k_get_rays(const float* __restrict__ poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t W,
+                           const int64_t* __restrict__ inds, uint32_t N, float* __restrict__ rays_o, float* __restrict__ rays_d,
+                           float* __restrict__ out_i, float* __restrict__ out_j) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * N) return;
+    const uint32_t b = t / N, n = t - b * N;
+    const uint32_t idx = inds ? (uint32_t)inds[n] : n;
+    float P[12];
+    #pragma unroll
+    for (int k = 0; k < 12; k++) P[k] = __ldg(poses + 16 * (size_t)b + k);
+    float ox, oy, oz, dx, dy, dz, i, j;
+    pixel_ray(P, fx, fy, cx, cy, idx % W, idx / W, ox, oy, oz, dx, dy, dz, i, j);
+    rays_o[3 * (size_t)t] = ox; rays_o[3 * (size_t)t + 1] = oy; rays_o[3 * (size_t)t + 2] = oz;
+    rays_d[3 * (size_t)t] = dx; rays_d[3 * (size_t)t + 1] = dy; rays_d[3 * (size_t)t + 2] = dz;
+    if (b == 0) {
+        if (out_i) out_i[n] = i;
+        if (out_j) out_j[n] = j;
+    }
+}
+
 __global__ void k_rays_init(RayInit ri, RayState st) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= ri.N) return;
@@ -154,7 +189,6 @@ __global__ void k_rays_init(RayInit ri, RayState st) {
         ox = ri.rays_o[3 * (size_t)n]; oy = ri.rays_o[3 * (size_t)n + 1]; oz = ri.rays_o[3 * (size_t)n + 2];
         dx = ri.rays_d[3 * (size_t)n]; dy = ri.rays_d[3 * (size_t)n + 1]; dz = ri.rays_d[3 * (size_t)n + 2];
     } else {
-        // utils.py:300-352: i = x + 0.5, j = y + 0.5; dir = normalize([(i-cx)/fx, (j-cy)/fy, 1]) @ R^T
         float P[12], fx = ri.fx, fy = ri.fy, cx = ri.cx, cy = ri.cy;
         if (ri.dyn) {           // per-frame scalars from device memory (CUDA-graph replay): 16 broadcast loads
             #pragma unroll
@@ -165,15 +199,8 @@ __global__ void k_rays_init(RayInit ri, RayState st) {
             for (int k = 0; k < 12; k++) P[k] = ri.pose[k];
         }
         const uint32_t py = n / ri.W, px = n - py * ri.W;
-        const float i = __fadd_rn((float)px, 0.5f), j = __fadd_rn((float)py, 0.5f);
-        const float xs = __fdiv_rn(__fsub_rn(i, cx), fx);
-        const float ys = __fdiv_rn(__fsub_rn(j, cy), fy);
-        const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(xs, xs), __fmul_rn(ys, ys)), 1.0f));
-        const float ux = __fdiv_rn(xs, nrm), uy = __fdiv_rn(ys, nrm), uz = __fdiv_rn(1.0f, nrm);
-        dx = P[0] * ux + P[1] * uy + P[2] * uz;
-        dy = P[4] * ux + P[5] * uy + P[6] * uz;
-        dz = P[8] * ux + P[9] * uy + P[10] * uz;
-        ox = P[3]; oy = P[7]; oz = P[11];
+        float i, j;
+        pixel_ray(P, fx, fy, cx, cy, px, py, ox, oy, oz, dx, dy, dz, i, j);
     }
     st.rays_o[3 * (size_t)n] = ox; st.rays_o[3 * (size_t)n + 1] = oy; st.rays_o[3 * (size_t)n + 2] = oz;
     st.rays_d[3 * (size_t)n] = dx; st.rays_d[3 * (size_t)n + 1] = dy; st.rays_d[3 * (size_t)n + 2] = dz;
@@ -367,6 +394,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) k_field_fp32(ModelDev m, Fie
     const uint32_t M = io.M_dev ? *io.M_dev : io.M_host;
     const int tid = threadIdx.x;
     const int H = m.H, G = m.G;
+    const bool sigma_only = !io.out4 && !io.rgbs;      // density query (grid maintenance): skip the geometry features and the colour net
 
     for (uint32_t tile = blockIdx.x; (uint64_t)tile * TILE_S < M; tile += gridDim.x) {
         const uint32_t base = tile * TILE_S;
@@ -382,7 +410,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) k_field_fp32(ModelDev m, Fie
                     dx = __ldg(io.rays_d + 3 * (size_t)ray); dy = __ldg(io.rays_d + 3 * (size_t)ray + 1); dz = __ldg(io.rays_d + 3 * (size_t)ray + 2);
                 } else {
                     x = io.xyzs[3 * (size_t)i]; y = io.xyzs[3 * (size_t)i + 1]; z = io.xyzs[3 * (size_t)i + 2];
-                    dx = io.dirs[3 * (size_t)i]; dy = io.dirs[3 * (size_t)i + 1]; dz = io.dirs[3 * (size_t)i + 2];
+                    if (io.dirs) { dx = io.dirs[3 * (size_t)i]; dy = io.dirs[3 * (size_t)i + 1]; dz = io.dirs[3 * (size_t)i + 2]; }
                 }
             }
             misc[0 * 128 + tid] = to_unit(x, m.bound);
@@ -431,6 +459,14 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) k_field_fp32(ModelDev m, Fie
         dense_tile(F, 64, m.w + m.s_wt0, H, H, P, nullptr, true, wstage);
         dense_tile(P, H, m.w + m.s_wt1, H, H, Q, nullptr, true, wstage);
         dense_small(Q, H, m.w + m.s_w2s, 1, misc + 8 * 128, misc + 12 * 128);
+        if (sigma_only) {
+            if (tid < TILE_S && base + tid < M) {
+                io.sigmas[base + tid] = expf(misc[8 * 128 + tid]);
+                if (io.ambient) { io.ambient[2 * (size_t)(base + tid)] = misc[6 * 128 + tid]; io.ambient[2 * (size_t)(base + tid) + 1] = misc[7 * 128 + tid]; }
+            }
+            __syncthreads();
+            continue;
+        }
         dense_tile(Q, H, m.w + m.s_wt2g, G, G, P + 16 * 128, nullptr, false, wstage);   // geo -> P rows 16..16+G
         // ---- SH(dir) -> P rows 0..15 --------------------------------------------------------------
         if (tid < TILE_S) {
@@ -863,6 +899,19 @@ GF_API uint64_t gf_model_packed_bytes(const GfModel* m) { return m ? (uint64_t)m
 
 GF_API uint64_t gf_render_workspace_bytes(uint32_t N) { return (uint64_t)carve(nullptr, N).bytes; }
 
+// get_rays (modules/radnerfs/utils.py:282-363) for B poses and a list of N flat pixel indices (NULL: N must be H*W, all pixels in
+// row-major order).  poses: device [B,4,4] c2w; outputs caller-allocated: rays_o / rays_d [B,N,3]; i / j [N] pixel-centre coordinates or NULL.
+GF_API int gf_get_rays(const float* poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W, const int64_t* inds,
+                       uint32_t N, float* rays_o, float* rays_d, float* i, float* j, gf_stream_t stream) {
+    GF_REQUIRE(poses && rays_o && rays_d, "get_rays: null pointer");
+    GF_REQUIRE(H >= 1 && W >= 1 && (uint64_t)H * W < (1ull << 31), "get_rays: bad H/W");
+    GF_REQUIRE(inds || N == H * W, "get_rays: without an index list N must be H*W");
+    GF_REQUIRE((uint64_t)B * N < (1ull << 32), "get_rays: B*N too large");
+    if (B == 0 || N == 0) return GF_OK;
+    k_get_rays<<<div_up(B * N, 256), 256, 0, ST(stream)>>>(poses, B, fx, fy, cx, cy, W, inds, N, rays_o, rays_d, i, j);
+    return check_launch("get_rays");
+}
+
 GF_API uint64_t gf_field_workspace_bytes(uint32_t M, uint32_t precision) {
     return 1024 + (precision ? (uint64_t)field_tc_scratch_bytes(M) : 0);
 }
@@ -873,7 +922,8 @@ GF_API uint64_t gf_field_workspace_bytes(uint32_t M, uint32_t precision) {
 // for precision 1, the hand-off buffers between the two tcgen05 kernels).  The model is not modified: re-entrant across streams.
 GF_API int gf_field_forward(const GfModel* model, const float* xyzs, const float* dirs, const float* cond_feat, uint32_t M, float* sigmas,
                             float* rgbs, float* ambient, uint32_t precision, void* workspace, uint64_t workspace_bytes, gf_stream_t stream) {
-    GF_REQUIRE(model && xyzs && dirs && cond_feat && sigmas && rgbs, "field_forward: null pointer");
+    GF_REQUIRE(model && xyzs && cond_feat && sigmas, "field_forward: null pointer");
+    GF_REQUIRE(dirs || !rgbs, "field_forward: dirs may be NULL only for a density query (rgbs == NULL)");
     GF_REQUIRE(precision <= 1, "field_forward: precision must be 0 (fp32) or 1 (fp16 tensor cores)");
     if (M == 0) return GF_OK;
     GF_REQUIRE(workspace && ((uintptr_t)workspace & 255) == 0, "field_forward: workspace must be a 256-byte aligned device pointer");

@@ -166,8 +166,10 @@ class NeRFRenderer(nn.Module):
         self.density_grid[seen == 0] = -1
 
     @torch.no_grad()
-    def update_extra_state(self, decay=0.95, S=128):
-        """EMA-max update of the occupancy grid from the current field at one jittered point per cell, dilation, bitfield repack."""
+    def update_extra_state(self, decay=0.95, S=128, precision=None):
+        """EMA-max update of the occupancy grid from the current field at one jittered point per cell, dilation, bitfield repack.
+        The C * H^3 density queries -- the whole cost of the routine -- go through the packed model's field kernels (`gf_field_forward`,
+        sigma-only: no colour net) when the configuration is inside the fused envelope, in `precision` (default: the model's render precision)."""
         if not self.cuda_ray:
             return
         dev = self.density_bitfield.device
@@ -179,7 +181,10 @@ class NeRFRenderer(nn.Module):
             bound, half_cell = self._cascade_extent(cas)
             pts = centre * (bound - half_cell)
             pts = pts + (torch.rand_like(pts) * 2 - 1) * half_cell
-            sigma = self.density(pts, enc_a)['sigma'].reshape(-1).detach()
+            if self._fused_supported():
+                sigma = self.field_forward(pts, None, enc_a, precision=precision, sigma_only=True)[0]
+            else:
+                sigma = self.density(pts, enc_a)['sigma'].reshape(-1).detach()
             fresh[cas, morton] = sigma.to(fresh.dtype) * self.density_scale
         fresh = raymarching.morton3D_dilation(fresh)
         live = (self.density_grid >= 0) & (fresh >= 0)
@@ -257,13 +262,16 @@ class NeRFRenderer(nn.Module):
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
         return self._ws, need
 
-    def field_forward(self, xyzs, dirs, cond_feat, precision=None):
-        """sigma, rgb, ambient for raw samples through the packed model (== self(...) of the reference loop)."""
+    def field_forward(self, xyzs, dirs, cond_feat, precision=None, sigma_only=False):
+        """sigma, rgb, ambient for raw samples through the packed model (== self(...) of the reference loop).
+        sigma_only=True (dirs may be None): the density query of the grid maintenance (radnerf.py:107-127); the colour net is skipped
+        and rgb is returned as None."""
         model = self.gf_model()
-        xyzs, dirs = xyzs.float().contiguous(), dirs.float().contiguous()
+        xyzs = xyzs.float().contiguous()
+        dirs = None if (dirs is None or sigma_only) else dirs.float().contiguous()
         M = xyzs.shape[0]
         sig = torch.empty(M, dtype=torch.float32, device=xyzs.device)
-        rgb = torch.empty(M, 3, dtype=torch.float32, device=xyzs.device)
+        rgb = None if sigma_only else torch.empty(M, 3, dtype=torch.float32, device=xyzs.device)
         amb = torch.empty(M, 2, dtype=torch.float32, device=xyzs.device)
         cf = cond_feat.float().contiguous().view(-1)
         prec = PRECISIONS[precision or self.precision]

@@ -43,31 +43,22 @@ def custom_meshgrid(*args):
 
 
 def get_audio_features(features, att_mode, index, smo_win_size=5):
-    """utils.py:71-104 (the reference reads smo_win_size from the global hparams)."""
+    """Window of per-frame condition features around frame `index` (utils.py:71-104; the reference reads smo_win_size from the
+    global hparams).  att_mode 0: the frame itself; 1: the `smo_win_size` frames before it; 2: a centred window.  Frames outside
+    the sequence are zero rows.  Built by index arithmetic (one gather + one mask), no concatenation."""
     if att_mode == 0:
         return features[[index]]
     if att_mode == 1:
-        left = index - smo_win_size
-        pad_left = max(0, -left)
-        left = max(left, 0)
-        auds = features[left:index]
-        if pad_left > 0:
-            auds = torch.cat([torch.zeros(pad_left, *auds.shape[1:], device=auds.device, dtype=auds.dtype), auds], dim=0)
-        return auds
-    if att_mode == 2:
-        left = index - smo_win_size // 2
-        right = index + (smo_win_size - smo_win_size // 2)
-        pad_left = max(0, -left)
-        left = max(left, 0)
-        pad_right = max(0, right - features.shape[0])
-        right = min(right, features.shape[0])
-        auds = features[left:right]
-        if pad_left > 0:
-            auds = torch.cat([torch.zeros_like(auds[:pad_left]), auds], dim=0)
-        if pad_right > 0:
-            auds = torch.cat([auds, torch.zeros_like(auds[:pad_right])], dim=0)
-        return auds
-    raise NotImplementedError(f'wrong att_mode: {att_mode}')
+        lo, hi = index - smo_win_size, index
+    elif att_mode == 2:
+        lo, hi = index - smo_win_size // 2, index + smo_win_size - smo_win_size // 2
+    else:
+        raise NotImplementedError(f'wrong att_mode: {att_mode}')
+    n = features.shape[0]
+    idx = torch.arange(lo, hi, device=features.device)
+    inside = (idx >= 0) & (idx < n)
+    win = features[idx.clamp(0, n - 1)]
+    return win * inside.view(-1, *([1] * (features.dim() - 1))).to(win.dtype)
 
 
 def matrix_to_euler_angles_xyz(matrix):
@@ -94,49 +85,48 @@ def get_bg_coords(H, W, device):
     return torch.cat([xs.reshape(-1, 1), ys.reshape(-1, 1)], dim=-1).unsqueeze(0)
 
 
+def pixel_indices(H, W, N=-1, patch_size=1, rect=None, device='cpu'):
+    """Flat (row-major, y * W + x) pixel indices of one ray batch, or None for the whole image -- the three sampling modes of the
+    reference's get_rays (utils.py:303-341), by index arithmetic: random pixels (with repetition), random patch_size^2 patches
+    (top-left corners drawn rows first, then columns, so a seeded torch RNG selects the same pixels as the reference), or every
+    pixel of the rows x columns box rect = (r0, r1, c0, c1) in ascending order."""
+    if rect is not None:
+        r0, r1, c0, c1 = rect
+        return (torch.arange(r0, r1, device=device).view(-1, 1) * W + torch.arange(c0, c1, device=device).view(1, -1)).reshape(-1)
+    if N <= 0:
+        return None
+    N = min(N, H * W)
+    if patch_size > 1:
+        k = N // (patch_size ** 2)
+        top = torch.randint(0, H - patch_size, size=[k], device=device)
+        left = torch.randint(0, W - patch_size, size=[k], device=device)
+        ar = torch.arange(patch_size, device=device)
+        return ((top.view(-1, 1, 1) + ar.view(1, -1, 1)) * W + (left.view(-1, 1, 1) + ar.view(1, 1, -1))).reshape(-1)
+    return torch.randint(0, H * W, size=[N], device=device)
+
+
 def get_rays(poses, intrinsics, H, W, N=-1, patch_size=1, rect=None):
-    """utils.py:282-363.  poses [B,4,4] c2w, intrinsics (fx,fy,cx,cy) -> dict(rays_o, rays_d, inds, i, j)."""
+    """Drop-in for modules/radnerfs/utils.py:282-363: poses [B,4,4] c2w (CUDA), intrinsics (fx, fy, cx, cy) ->
+    dict(rays_o [B,n,3], rays_d [B,n,3], inds [B,n], i [B,n], j [B,n]).  The rays come from the `gf_get_rays` operator of
+    libgfrender (the same pixel -> ray arithmetic as the fused renderer's in-kernel ray generation)."""
+    from . import _lib
+    _lib.require_cuda()
     device = poses.device
     B = poses.shape[0]
-    fx, fy, cx, cy = intrinsics
-    if rect is not None:
-        xmin, xmax, ymin, ymax = rect
-        N = (xmax - xmin) * (ymax - ymin)
-    i, j = custom_meshgrid(torch.linspace(0, W - 1, W, device=device), torch.linspace(0, H - 1, H, device=device))
-    i = i.t().reshape([1, H * W]).expand([B, H * W]) + 0.5
-    j = j.t().reshape([1, H * W]).expand([B, H * W]) + 0.5
-    results = {}
-    if N > 0:
-        N = min(N, H * W)
-        if patch_size > 1:
-            num_patch = N // (patch_size ** 2)
-            inds_x = torch.randint(0, H - patch_size, size=[num_patch], device=device)
-            inds_y = torch.randint(0, W - patch_size, size=[num_patch], device=device)
-            inds = torch.stack([inds_x, inds_y], dim=-1)
-            pi, pj = custom_meshgrid(torch.arange(patch_size, device=device), torch.arange(patch_size, device=device))
-            offsets = torch.stack([pi.reshape(-1), pj.reshape(-1)], dim=-1)
-            inds = (inds.unsqueeze(1) + offsets.unsqueeze(0)).view(-1, 2)
-            inds = (inds[:, 0] * W + inds[:, 1]).expand([B, N])
-        elif rect is not None:
-            mask = torch.zeros(H, W, dtype=torch.bool, device=device)
-            mask[xmin:xmax, ymin:ymax] = 1
-            inds = torch.where(mask.view(-1))[0].unsqueeze(0)
-        else:
-            inds = torch.randint(0, H * W, size=[N], device=device).expand([B, N])
-        i = torch.gather(i, -1, inds)
-        j = torch.gather(j, -1, inds)
-    else:
-        inds = torch.arange(H * W, device=device).expand([B, H * W])
-    results['i'], results['j'], results['inds'] = i, j, inds
-    zs = torch.ones_like(i)
-    xs = (i - cx) / fx * zs
-    ys = (j - cy) / fy * zs
-    directions = torch.stack((xs, ys, zs), dim=-1)
-    directions = directions / torch.norm(directions, dim=-1, keepdim=True)
-    rays_d = directions @ poses[:, :3, :3].transpose(-1, -2)
-    rays_o = poses[..., :3, 3][..., None, :].expand_as(rays_d)
-    results['rays_o'], results['rays_d'] = rays_o, rays_d
-    return results
+    inds = pixel_indices(H, W, N, patch_size, rect, device)
+    n = H * W if inds is None else inds.numel()
+    P = poses.detach().float().contiguous()
+    rays_o = torch.empty(B, n, 3, dtype=torch.float32, device=device)
+    rays_d = torch.empty(B, n, 3, dtype=torch.float32, device=device)
+    pi = torch.empty(n, dtype=torch.float32, device=device)
+    pj = torch.empty(n, dtype=torch.float32, device=device)
+    fx, fy, cx, cy = (float(v) for v in intrinsics)
+    idx = None if inds is None else inds.to(torch.int64).contiguous()
+    _lib.check(_lib.lib().gf_get_rays(_lib.ptr(P), B, fx, fy, cx, cy, H, W, _lib.ptr(idx), n, _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(pi),
+                                      _lib.ptr(pj), _lib.stream_ptr()), "gf_get_rays")
+    if inds is None:
+        inds = torch.arange(H * W, device=device)
+    return {'rays_o': rays_o, 'rays_d': rays_d, 'inds': inds.expand(B, n), 'i': pi.expand(B, n), 'j': pj.expand(B, n)}
 
 
 def orbit_pose(radius=3.35, yaw_deg=0.0):

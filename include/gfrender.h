@@ -248,8 +248,15 @@ typedef struct GfOut {
                                     iteration whose offered slots contain it; a slot > S_total was never observed by that loop. */
 } GfOut;
 
+/* get_rays (modules/radnerfs/utils.py:282-363): pixel-centre pinhole rays of B poses (device [B,4,4] c2w) for N flat pixel indices
+ * (inds == NULL: N = H*W, every pixel in row-major order).  Outputs caller-allocated: rays_o, rays_d [B,N,3]; i, j [N] or NULL. */
+GF_API int gf_get_rays(const float* poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
+                       const int64_t* inds, uint32_t N, float* rays_o, float* rays_d, float* i, float* j, gf_stream_t stream);
+
 /* Standalone field evaluation = the `self(xyzs, dirs, cond_feat, ind_code)` call inside the reference
  * loop (renderer.py:342 -> radnerf.py:73-105).  xyzs, dirs [M,3]; sigmas [M]; rgbs [M,3]; ambient [M,2] or NULL. */
+/* rgbs == NULL: density query (NeRFRenderer.density, radnerf.py:107-127): the colour net is skipped, dirs may be NULL.
+ * workspace: caller-owned device scratch of gf_field_workspace_bytes(M, precision) bytes, 256-byte aligned. */
 GF_API uint64_t gf_field_workspace_bytes(uint32_t M, uint32_t precision);
 GF_API int gf_field_forward(const GfModel* model, const float* xyzs, const float* dirs, const float* cond_feat, uint32_t M,
                             float* sigmas, float* rgbs, float* ambient, uint32_t precision, void* workspace,

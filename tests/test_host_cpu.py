@@ -33,10 +33,26 @@ def test_state_dict_matches_reference_inventory():
 def test_rays_poses_bgcoords_match_oracle_restatement():
     from geneface_b200 import synthetic, utils
     from oracle import field as OF
+    import pytest
     fi = synthetic.frame_inputs(33, 47, yaw_deg=7.0, device='cpu')
-    r = utils.get_rays(fi['pose'], fi['intrinsics'], 33, 47)
-    ro, rd = OF.get_rays(fi['pose'][0].numpy(), fi['intrinsics'], 33, 47)
-    assert np.abs(r['rays_d'][0].numpy() - rd).max() < 3e-7 and np.array_equal(r['rays_o'][0].numpy(), ro)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):                       # get_rays is a libgfrender operator: no CPU fallback
+            utils.get_rays(fi['pose'], fi['intrinsics'], 33, 47)
+    # the three pixel-sampling modes select exactly the pixels the reference's get_rays selects under the same torch seed
+    from oracle import ref_model
+    if ref_model.available():
+        ns = ref_model.load()
+        for kw in (dict(N=40), dict(N=64, patch_size=4), dict(rect=(2, 7, 3, 9)), dict(N=10 ** 6)):
+            torch.manual_seed(3)
+            ref = ns.utils.get_rays(torch.eye(4)[None], (20., 20., 8., 8.), 16, 24, **kw)['inds'][0]
+            torch.manual_seed(3)
+            ours = utils.pixel_indices(16, 24, kw.get('N', -1), kw.get('patch_size', 1), kw.get('rect'))
+            assert torch.equal(ref, ours), kw
+        f = torch.randn(9, 1, 204)
+        ns.hparams['smo_win_size'] = 5
+        for mode in (0, 1, 2):
+            for idx in range(9):
+                assert torch.equal(utils.get_audio_features(f, mode, idx, 5), ns.utils.get_audio_features(f, mode, idx)), (mode, idx)
     assert np.allclose(utils.convert_poses(fi['pose'])[0].numpy(), OF.convert_poses(fi['pose'][0].numpy()), atol=1e-6)
     assert np.allclose(utils.get_bg_coords(33, 47, 'cpu')[0].numpy(), OF.get_bg_coords(33, 47), atol=1e-7)
     p0 = utils.orbit_pose(3.35, 0.0)

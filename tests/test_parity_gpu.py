@@ -651,3 +651,29 @@ def test_fused_field_on_hash_and_smoothstep_grids(grid_type, interp):
         assert_close(amb.cpu().numpy(), a_t.cpu().numpy(), rel=1e-3, abs_=2e-5, what=f"ambient_pos {prec}")
         assert_close(sig.cpu().numpy(), s_t.cpu().numpy(), rel=rel, abs_=1e-6, what=f"sigma {prec}")
         assert_close(rgb.cpu().numpy(), c_t.cpu().numpy(), rel=1e-3, abs_=2e-4, what=f"rgb {prec}")
+
+
+@pytest.mark.gpu
+def test_get_rays_operator_vs_oracle_and_the_reference():
+    """utils.get_rays (the gf_get_rays operator + index arithmetic) against the numpy restatement and, where oracle/_ref travels,
+    the reference's own get_rays under the same torch seed: same pixels, same (i, j), directions within 1 ulp-class (3e-7)."""
+    from geneface_b200 import synthetic, utils
+    from oracle import field as OF, ref_model
+    H, W = 33, 47
+    fi = synthetic.frame_inputs(H, W, yaw_deg=7.0)
+    r = utils.get_rays(fi['pose'], fi['intrinsics'], H, W)
+    ro, rd = OF.get_rays(fi['pose'][0].cpu().numpy(), fi['intrinsics'], H, W)
+    assert np.abs(r['rays_d'][0].cpu().numpy() - rd).max() < 3e-7 and np.array_equal(r['rays_o'][0].cpu().numpy(), ro)
+    assert r['inds'].shape == (1, H * W) and torch.equal(r['inds'][0].cpu(), torch.arange(H * W))
+    if not ref_model.available():
+        return
+    ns = ref_model.load()
+    poses = torch.cat([fi['pose'], synthetic.frame_inputs(H, W, yaw_deg=-3.0)['pose']])
+    for kw in (dict(), dict(N=500), dict(N=640, patch_size=8), dict(rect=(4, 20, 10, 40))):
+        torch.manual_seed(5)
+        a = utils.get_rays(poses, fi['intrinsics'], H, W, **kw)
+        torch.manual_seed(5)
+        b = ns.utils.get_rays(poses, fi['intrinsics'], H, W, **kw)
+        for k in ('inds', 'i', 'j'):
+            assert torch.equal(a[k].expand_as(b[k]).float(), b[k].float()), (k, kw)
+        assert torch.equal(a['rays_o'], b['rays_o'].contiguous()) and (a['rays_d'] - b['rays_d']).abs().max().item() < 3e-7, kw
