@@ -111,7 +111,7 @@ __device__ __forceinline__ float perturbed_t0(const MarchConst& m, float near, f
 __global__ void k_march_train_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                     const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps,
                                     uint32_t N, uint32_t C, uint32_t H, const float* __restrict__ nears,
-                                    const float* __restrict__ fars, const float* __restrict__ noises, int* __restrict__ counts) {
+                                    const float* __restrict__ fars, const float* __restrict__ noises, int* __restrict__ rays) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const MarchConst m = make_march_const(bound, dt_gamma, max_steps, C, H, grid);
@@ -126,20 +126,28 @@ __global__ void k_march_train_count(const float* __restrict__ rays_o, const floa
         num_steps++;
         t = __fadd_rn(t, p.dt);
     }
-    counts[n] = (int)num_steps;
+    rays[3 * (size_t)n + 2] = (int)num_steps;      // the count's final place in row n = (ray id, offset, count)
 }
 
-// Single block: exclusive scan of counts (stored in rays[:,2] by the caller's layout below).
-__global__ void k_march_train_scan(const int* __restrict__ counts, uint32_t N, int* __restrict__ rays, int* __restrict__ counter) {
+// Single block: exclusive scan of the per-ray counts (already in column 2 of `rays`) into sample offsets (column 1).
+// Offsets are handed out in ROTATED ray order (first ray = rot): when the sample total exceeds M (the running mean of the previous
+// steps, raymarching.py:225-228) the rays that lose their samples are the last ones in allocation order -- in the reference whichever
+// lose its atomic race, here a contiguous run starting at a per-call pseudo-random ray instead of always the highest indices (which
+// would systematically starve the bottom rows of an ordered ray set such as the lips rectangle).  rot is derived from the first
+// perturbation noise (0 when perturb is off: plain index order).  Row n always describes ray n; counter[1] only reports N.
+__global__ void k_march_train_scan(uint32_t N, int* rays, int* counter, const float* __restrict__ noises) {
     __shared__ int warp_sums[32];
     __shared__ int carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int base_point = counter[0], base_ray = counter[1];
+    const int base_point = counter[0];
+    const uint32_t rot = N > 1 ? (__float_as_uint(noises[0]) >> 3) % N : 0;
     if (tid == 0) carry = 0;
     __syncthreads();
     for (uint32_t start = 0; start < N; start += blockDim.x) {
-        const uint32_t n = start + tid;
-        const int c = n < N ? counts[n] : 0;
+        const uint32_t p = start + tid;
+        uint32_t n = p + rot;
+        if (n >= N) n -= N;
+        const int c = p < N ? rays[3 * (size_t)n + 2] : 0;
         int v = c;
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -159,11 +167,9 @@ __global__ void k_march_train_scan(const int* __restrict__ counts, uint32_t N, i
         }
         __syncthreads();
         const int incl = v + (wid ? warp_sums[wid - 1] : 0) + carry;
-        if (n < N) {
-            int* row = rays + 3 * (size_t)(base_ray + n);
-            row[0] = (int)n;
-            row[1] = base_point + incl - c;
-            row[2] = c;
+        if (p < N) {
+            rays[3 * (size_t)n] = (int)n;
+            rays[3 * (size_t)n + 1] = base_point + incl - c;
         }
         __syncthreads();
         if (tid == blockDim.x - 1) carry = incl;
@@ -171,7 +177,7 @@ __global__ void k_march_train_scan(const int* __restrict__ counts, uint32_t N, i
     }
     if (tid == 0) {
         counter[0] = base_point + carry;
-        counter[1] = base_ray + (int)N;
+        counter[1] += (int)N;
     }
 }
 
@@ -183,8 +189,8 @@ __global__ void k_march_train_write(const float* __restrict__ rays_o, const floa
                                     float* __restrict__ dirs, float* __restrict__ deltas) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
-    const int base_ray = counter[1] - (int)N;   // the scan already advanced counter[1] by N
-    const int* row = rays + 3 * (size_t)(base_ray + n);
+    (void)counter;
+    const int* row = rays + 3 * (size_t)n;
     const uint32_t point_index = (uint32_t)row[1], num_steps = (uint32_t)row[2];
     if (num_steps == 0 || point_index + num_steps > M) return;
     const MarchConst m = make_march_const(bound, dt_gamma, max_steps, C, H, grid);
@@ -432,16 +438,13 @@ GF_API int gf_march_rays_train(const float* rays_o, const float* rays_d, const u
                "march_rays_train: null pointer");
     GF_REQUIRE(C >= 1 && C <= 8 && H >= 1 && max_steps >= 1, "march_rays_train: bad C/H/max_steps");
     if (N == 0) return GF_OK;
-    // pass 1: per-ray sample counts, parked in the last N ints of the caller's [N,3] `rays`
-    // buffer.  The scan writes row n (ints 3n..3n+2), which can only land on counts[k] with
-    // k <= n -- already consumed by then -- so no extra workspace is needed (counter[1] == 0 on
-    // entry, as at every reference call site: renderer.py:298-299).
-    int* counts = rays + 2 * (size_t)N;   // last N ints of the [N,3] buffer
+    // pass 1: per-ray sample counts straight into column 2 of `rays`; pass 2: offsets (column 1) by a single-block scan; pass 3: samples.
+    // Row n of `rays` always describes ray n (the reference fills rows in atomic-arrival order, raymarching.cu:452-457).
     k_march_train_count<<<div_up(N, NT), NT, 0, ST(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
-                                                               nears, fars, noises, counts);
+                                                               nears, fars, noises, rays);
     int rc = check_launch("march_rays_train(count)");
     if (rc) return rc;
-    k_march_train_scan<<<1, 1024, 0, ST(stream)>>>(counts, N, rays, counter);
+    k_march_train_scan<<<1, 1024, 0, ST(stream)>>>(N, rays, counter, noises);
     rc = check_launch("march_rays_train(scan)");
     if (rc) return rc;
     k_march_train_write<<<div_up(N, NT), NT, 0, ST(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,

@@ -119,8 +119,11 @@ class _march_rays_train(Function):
     @staticmethod
     def forward(ctx, rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter=None, mean_count=-1,
                 perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024):
-        """raymarching.py:186-258.  Layout differs from the reference only in being deterministic
-        (rays appear in index order; the reference's order is whatever its atomics produce)."""
+        """raymarching.py:186-258.  Layout differs from the reference only in being deterministic: row n of `rays` is ray n (the
+        reference's row order is whatever its atomics produce) and sample offsets are an exclusive scan of the per-ray counts
+        starting at ray rot = bits(noises[0]) % N.  When the sample total exceeds M = mean_count (the normal training regime,
+        raymarching.py:225-228) the rays that lose their samples are therefore a pseudo-random contiguous run that changes every
+        step -- like the reference's race losers -- not systematically the highest ray indices."""
         rays_o = _cuda_f32(rays_o).view(-1, 3)
         rays_d = _cuda_f32(rays_d).view(-1, 3)
         if not density_bitfield.is_cuda:

@@ -8,7 +8,8 @@ inference/nerfs/base_nerf_infer.py:131-179 (BASELINE.json configs[3]: 300 frames
 
 Single GPU:   python scripts/render_sequence.py --synthetic --frames 300 --out /tmp/frames
 Multi GPU:    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 scripts/render_sequence.py --synthetic --frames 300 --out /tmp/frames
-With data:    ... --data <binary_data_dir containing trainval_dataset.npy> --lm3d <pred_lm3d.npy> --ckpt <state_dict.pt>
+With data:    ... --data <binary_data_dir containing trainval_dataset.npy> --lm3d <pred_lm3d.npy> --ckpt <checkpoint.ckpt | state_dict.pt>
+              [--smooth-kernel 7] [--bg white|black|<image>]   (the reference's infer_* defaults, egs/egs_bases/radnerf/base.yaml:110-116)
 Prints one JSON line per run (rank 0): frames, seconds, frames/s including PNG encoding, bytes written.
 """
 import argparse
@@ -20,12 +21,47 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def unwrap_checkpoint(ckpt, model_name="model"):
+    """A reference trainer checkpoint -> the model's state_dict (utils/commons/ckpt_utils.py:26-60): {'state_dict': {...}} with either
+    'model.'-prefixed flat keys or a nested {'model': state_dict}; a bare state_dict passes through."""
+    sd = ckpt.get("state_dict", ckpt) if isinstance(ckpt, dict) else ckpt
+    if isinstance(sd, dict) and model_name in sd and isinstance(sd[model_name], dict):
+        return sd[model_name]
+    if isinstance(sd, dict) and any(k.startswith(model_name + ".") for k in sd):
+        return {k[len(model_name) + 1:]: v for k, v in sd.items() if k.startswith(model_name + ".")}
+    return sd
+
+
+def background_image(spec, dataset_bg, H, W):
+    """infer_bg_img_fname semantics (tasks/radnerfs/dataset_utils.py:62-78): '' = dataset background, 'white', 'black', else an image file
+    (BGR(A) -> RGB, resized to W x H, /255).  Returns float32 [H, W, 3] in [0, 1]."""
+    import numpy as np
+    if spec == "":
+        return np.asarray(dataset_bg, np.float32)
+    if spec == "white":
+        return np.ones((H, W, 3), np.float32)
+    if spec == "black":
+        return np.zeros((H, W, 3), np.float32)
+    import cv2
+    img = cv2.imread(spec, cv2.IMREAD_UNCHANGED)
+    if img is None:
+        raise SystemExit("cannot read background image %s" % spec)
+    if img.shape[0] != H or img.shape[1] != W:
+        img = cv2.resize(img, (W, H), interpolation=cv2.INTER_AREA)
+    img = cv2.cvtColor(img, cv2.COLOR_BGRA2RGB if img.ndim == 3 and img.shape[2] == 4 else cv2.COLOR_BGR2RGB)
+    return img.astype(np.float32) / 255.0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--synthetic", action="store_true", help="random-weight May-configuration model and a synthetic pose/landmark sequence")
     ap.add_argument("--data", default=None, help="directory with trainval_dataset.npy")
     ap.add_argument("--lm3d", default=None, help=".npy with the predicted idexp_lm3d sequence [1, T, 204]")
-    ap.add_argument("--ckpt", default=None, help="torch state_dict of RADNeRFTorso (reference key names)")
+    ap.add_argument("--ckpt", default=None, help="RADNeRFTorso weights: a bare state_dict or a reference trainer checkpoint "
+                    "({'state_dict': {'model': ...}} / 'model.'-prefixed keys, utils/commons/ckpt_utils.py:26-60); loaded strictly")
+    ap.add_argument("--smooth-kernel", type=int, default=7, help="camera-path smoothing window (infer_smooth_camera_path_kernel_size, "
+                    "egs/egs_bases/radnerf/base.yaml:115-116: on, 7); 0 disables")
+    ap.add_argument("--bg", default="", help="infer_bg_img_fname (base.yaml:114): '' = the dataset background, 'white', 'black', or an image file")
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--out", default=None, help="directory for the PNG frames (omit to skip encoding)")
@@ -59,15 +95,17 @@ def main():
         poses = np.stack([orbit_pose(3.35, 10.0 * np.sin(2 * np.pi * f / 100.0)) for f in range(args.frames)])
     else:
         from geneface_b200.renderer import RADNeRFTorso
-        inp = ingress.SequenceInputs.load(args.data, prefix="val")
+        inp = ingress.SequenceInputs.load(args.data, prefix="val", smooth_kernel=args.smooth_kernel)
         H, W, intr = inp.H, inp.W, inp.intrinsics
         hp = synthetic.may_hparams()
         model = RADNeRFTorso(hp).to(dev).eval()
-        if rank == 0 and args.ckpt:
-            model.load_state_dict(torch.load(args.ckpt, map_location=dev), strict=False)
+        if args.ckpt is None:
+            raise SystemExit("--data needs --ckpt (refusing to render a real sequence with random weights)")
+        if rank == 0:
+            model.load_state_dict(unwrap_checkpoint(torch.load(args.ckpt, map_location=dev)), strict=True)   # missing / unexpected keys raise
         lm = np.load(args.lm3d)[0]
         poses, wins = inp.sequence(lm[:args.frames], args.clamp_std, hp['cond_win_size'], hp['smo_win_size'])
-        bg = torch.from_numpy(inp.bg_img).view(1, -1, 3).to(dev)
+        bg = torch.from_numpy(background_image(args.bg, inp.bg_img, H, W)).view(1, -1, 3).to(dev)
     sequence.broadcast_model_(model, src=0)                 # the only collective: parameters, once
     T = min(args.frames, wins.shape[0])
     start, end = sequence.partition_frames(T, world, rank)

@@ -163,6 +163,18 @@ def test_fused_frame_reproduces_the_reference_frames(name, precision):
         assert_close(res["torso_alpha_map"][:, 0].cpu().numpy(), g["torso_alpha_map"], what="torso_alpha_map")
         assert_close(res["torso_rgb_map"].view(-1, 3).cpu().numpy(), g["torso_rgb_map"], what="torso_rgb_map")
     print(f"{name} {precision}: worst scaled err", {k: f"{v:.2e}" for k, v in worst.items()})
+    # frame egress (base_nerf_infer.py:97-101: (rgb * 255).astype(uint8), truncation): the RGB8 frame packed by k_finish equals the
+    # truncated reference image, except where the reference value lies within 1e-3 (relative, the float bar) of a code boundary
+    with torch.no_grad():
+        cf = model.cal_cond_feat(fi["cond"])
+        out = model.render_fused(cf, 1, N, rays_o=ro, rays_d=rd, bg_color=fi["bg_color"], bg_coords=bgc, torso_pose=poses6,
+                                 dt_gamma=float(g["dt_gamma"]), max_steps=int(g["max_steps"]), precision=precision, want=("rgb8",))
+    rgb8 = out["rgb8"].cpu().numpy().astype(np.int32)
+    ref255 = g["rgb_map"].astype(np.float64) * 255.0
+    code = np.floor(ref255).astype(np.int32)
+    near = np.abs(ref255 - np.round(ref255)) <= 1e-3 * ref255 + 255e-5
+    okpix = (rgb8 == code) | (near & (np.abs(rgb8 - code) <= 1))
+    assert okpix[good].all(), f"rgb8: {int((~okpix[good]).sum())} channels differ from trunc(reference * 255)"
 
 
 def _live_reference(model, hp, torso, fi, H, W, dt_gamma, max_steps):

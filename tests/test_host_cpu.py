@@ -285,3 +285,21 @@ def test_packed_frame_inputs_layout():
         assert torch.allclose(p[f, 1032:1036], torch.tensor(intr))
         assert torch.equal(p[f, 1036:], utils.convert_poses(poses[f:f + 1])[0])
     assert torch.count_nonzero(sequence.pack_frame_inputs(poses, conds, intr, torso=False)[:, 1036:]) == 0
+
+
+def test_render_sequence_checkpoint_unwrap_and_background_options():
+    """scripts/render_sequence.py: reference trainer checkpoints ({'state_dict': {'model': sd}} or 'model.'-prefixed flat keys,
+    utils/commons/ckpt_utils.py:26-60) unwrap to the model's state_dict (then loaded strictly); infer_bg_img_fname semantics."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("render_sequence", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "render_sequence.py"))
+    rs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rs)
+    sd = {"a.weight": torch.zeros(2), "b": torch.ones(1)}
+    assert rs.unwrap_checkpoint(sd) is sd
+    assert rs.unwrap_checkpoint({"state_dict": {"model": sd}, "global_step": 3}) is sd
+    flat = rs.unwrap_checkpoint({"state_dict": {"model.a.weight": sd["a.weight"], "model.b": sd["b"], "other.x": torch.zeros(1)}})
+    assert set(flat) == {"a.weight", "b"}
+    ds_bg = np.full((4, 6, 3), 0.25, np.float32)
+    assert rs.background_image("", ds_bg, 4, 6) is not None and np.array_equal(rs.background_image("", ds_bg, 4, 6), ds_bg)
+    assert rs.background_image("white", ds_bg, 4, 6).min() == 1.0 and rs.background_image("black", ds_bg, 4, 6).max() == 0.0

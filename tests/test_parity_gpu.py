@@ -134,6 +134,7 @@ def test_march_rays_train_and_composite_train(rm, oracle_ops):
     nears_np, fars_np = oracle_ops.near_far_from_aabb(o, d, aabb, 0.05)
     for max_steps, dt_gamma in ((16, 1 / 256), (64, 0.0)):
         noises = np.random.RandomState(6).rand(N).astype(np.float32)
+        noises[0] = 0.0            # allocation order is rotated by bits(noises[0]) (checked separately below): 0 = plain index order
         x_ref, d_ref, dl_ref, rays_ref, cnt_ref = oracle_ops.march_rays_train(o, d, bound, bf, C, H, nears_np, fars_np, noises, dt_gamma, max_steps)
         from geneface_b200 import _lib
         M = N * max_steps
@@ -157,6 +158,30 @@ def test_march_rays_train_and_composite_train(rm, oracle_ops):
                 c = rays_ref[i, 2]
                 assert bits_equal(x2n[r2n[i, 1]:r2n[i, 1] + c], x_ref[rays_ref[i, 1]:rays_ref[i, 1] + c])
                 assert bits_equal(l2n[r2n[i, 1]:r2n[i, 1] + c], dl_ref[rays_ref[i, 1]:rays_ref[i, 1] + c])
+        # rotated allocation order (overflow then drops a pseudo-random run of rays, not always the highest indices): same per-ray
+        # samples, offsets = exclusive scan of the counts starting at ray rot = (bits(noises[0]) >> 3) % N; with M too small the
+        # dropped rays are exactly those whose offset + count exceeds M (raymarching.cu:457)
+        nz = noises.copy(); nz[0] = 0.37
+        xr, _, dlr, rr, _ = oracle_ops.march_rays_train(o, d, bound, bf, C, H, nears_np, fars_np, nz, dt_gamma, max_steps)
+        Msmall = int(rr[:, 2].sum()) * 3 // 4
+        x3 = torch.zeros(Msmall, 3, device="cuda"); d3 = torch.zeros(Msmall, 3, device="cuda"); l3 = torch.zeros(Msmall, 2, device="cuda")
+        r3 = torch.empty(N, 3, dtype=torch.int32, device="cuda"); c3 = torch.zeros(2, dtype=torch.int32, device="cuda")
+        _lib.check(_lib.lib().gf_march_rays_train(_lib.ptr(cu(o)), _lib.ptr(cu(d)), _lib.ptr(cu(bf)), _lib.c_f32(bound), _lib.c_f32(dt_gamma), max_steps,
+                                                  N, C, H, Msmall, _lib.ptr(cu(nears_np)), _lib.ptr(cu(fars_np)), _lib.ptr(x3), _lib.ptr(d3), _lib.ptr(l3),
+                                                  _lib.ptr(r3), _lib.ptr(c3), _lib.ptr(cu(nz)), _lib.stream_ptr()))
+        r3n, x3n = r3.cpu().numpy(), x3.cpu().numpy()
+        rot = int((np.float32(0.37).view(np.uint32) >> 3) % N)
+        order = (np.arange(N) + rot) % N
+        exp_off = np.empty(N, np.int64)
+        exp_off[order] = np.concatenate([[0], np.cumsum(rr[order, 2])[:-1]])
+        assert np.array_equal(r3n[:, 0], np.arange(N)) and np.array_equal(r3n[:, 2], rr[:, 2]) and np.array_equal(r3n[:, 1], exp_off)
+        assert int(c3[0]) == int(rr[:, 2].sum()) and rot != 0
+        dropped = exp_off + rr[:, 2] > Msmall
+        assert dropped.any() and not dropped[order[0]] and dropped[order[-1]]       # the LAST rays in allocation order lose their samples
+        for i in range(0, N, 41):
+            c = rr[i, 2]
+            if c and not dropped[i]:
+                assert bits_equal(x3n[exp_off[i]:exp_off[i] + c], xr[rr[i, 1]:rr[i, 1] + c])
         # composite train fwd / bwd
         Mtot = int(cnt_ref[0])
         rs = np.random.RandomState(8)
