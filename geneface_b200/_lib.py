@@ -18,7 +18,7 @@ _SO = os.environ.get("GF_LIBGFRENDER") or os.path.join(_PKG, "libgfrender.so")
 _VARIANT = bool(os.environ.get("GF_LIBGFRENDER"))
 _INCLUDE = os.path.join(os.path.dirname(_PKG), "include")
 
-SOURCES = ["api.cu", "raymarch_ops.cu", "encoders.cu", "render_fused.cu", "field_tc_split.cu", "adnerf_ops.cu"]
+SOURCES = ["api.cu", "raymarch_ops.cu", "encoders.cu", "render_fused.cu", "field_tc_split.cu", "adnerf_ops.cu", "adnerf_mlp_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -121,6 +121,10 @@ _SIGS = {
     "gf_adnerf_raw2outputs": [c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "gf_adnerf_sample_pdf": [c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_int, c_vp, c_vp, c_vp],
     "gf_get_rays": [c_vp, c_u32, c_f32, c_f32, c_f32, c_f32, c_u32, c_u32, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "gf_adnerf_mlp_create": [c_vp, c_vp, c_vp],
+    "gf_adnerf_mlp_destroy": [c_vp],
+    "gf_adnerf_mlp_workspace_bytes": [c_vp, c_u32],
+    "gf_adnerf_mlp_forward": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_vp, c_vp, c_u64, c_vp],
     "gf_model_create": [c_vp, c_vp, c_vp],
     "gf_model_destroy": [c_vp],
     "gf_model_packed_bytes": [c_vp],
@@ -136,7 +140,8 @@ _SIGS = {
     "gf_device_ok": [],
 }
 _RESTYPE = {"gf_last_error": ctypes.c_char_p, "gf_model_destroy": None, "gf_model_packed_bytes": c_u64,
-            "gf_render_workspace_bytes": c_u64, "gf_field_workspace_bytes": c_u64}
+            "gf_render_workspace_bytes": c_u64, "gf_field_workspace_bytes": c_u64, "gf_adnerf_mlp_workspace_bytes": c_u64,
+            "gf_adnerf_mlp_destroy": None}
 
 EXPORTS = sorted(_SIGS)
 

@@ -7,16 +7,19 @@ Mirrors, with the reference's names, arguments and state_dict keys:
   modules/nerfs/adnerf/adnerf.py:9-44                ADNeRF
   modules/nerfs/commons/volume_rendering.py:9-282    raw2outputs, sample_pdf, render_rays, batchify_render_rays, render_dynamic_face
 
-The non-GEMM operators (rays, frequency embedding, alpha compositing with the background-colour last sample, inverse-CDF
-importance sampling + merge) are libgfrender kernels (csrc/adnerf_ops.cu) reached through the C ABI; the 8x256 / 3x128 MLPs are
-plain library GEMMs (torch F.linear, fp32).  When the network is this module's ADNeRF, render_rays evaluates the backbone in a
-FOLDED form that is algebraically identical to backbone.py:107-135 but never materialises the per-sample copies the reference
-concatenates: the per-frame audio feature becomes a bias of layers 0 and 5, the per-ray view embedding a per-ray bias of the
-first colour layer, and the position embedding is produced straight from (rays, z) by one kernel.
+Every operator of the path is a libgfrender kernel reached through the C ABI: rays, frequency embedding, alpha compositing with the
+background-colour last sample, inverse-CDF importance sampling + merge (csrc/adnerf_ops.cu), and the 8 x hid / 3 x hid/2 backbone
+itself on tcgen05 tensor cores (csrc/adnerf_mlp_tc.cu, `gf_adnerf_mlp_forward`: fp16 operands, fp32 accumulation).  When the network is
+this module's ADNeRF, render_rays evaluates the backbone in a FOLDED form that is algebraically identical to backbone.py:107-135 but never
+materialises the per-sample copies the reference concatenates: the per-frame audio feature becomes a bias of layers 0 and 5, the view
+embedding an extra K-chunk of the first colour layer, and the position embedding is produced straight from (rays, z) in the tensor-core
+operand layout.  `NeRFBackbone.forward` / `forward_folded` (torch, fp32) remain as the reference-form definitions used by the CPU tests
+and for inputs outside the fused envelope (per-sample conditions).
 
 Inference only (the C ABI operators have no backward): calling these functions with gradients enabled on inputs that require
 grad raises.  CUDA tensors only -- there is no CPU fallback.
 """
+import ctypes
 import math
 
 import torch
@@ -74,6 +77,13 @@ class FreqEmbedder(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------------ networks
+class GfAdnerfDesc(ctypes.Structure):
+    """include/gfrender.h: GfAdnerfDesc"""
+    _fields_ = [("hid", ctypes.c_uint32), ("cond_dim", ctypes.c_uint32), ("pos_multires", ctypes.c_uint32), ("view_multires", ctypes.c_uint32),
+                ("dens_w", ctypes.c_void_p * 8), ("dens_b", ctypes.c_void_p * 8), ("dens_out_w", ctypes.c_void_p), ("dens_out_b", ctypes.c_void_p),
+                ("col_w", ctypes.c_void_p * 3), ("col_b", ctypes.c_void_p * 3), ("col_out_w", ctypes.c_void_p), ("col_out_b", ctypes.c_void_p)]
+
+
 class AudioNet(nn.Module):
     """backbone.py:6-42: deepspeech window [B, 16, 29] -> conv1d x4 (stride 2) -> fc -> [B, out_dim]."""
 
@@ -147,6 +157,62 @@ class NeRFBackbone(nn.Module):
         for lin in self.color_linears:
             h = F.relu(lin(h))
         return torch.cat([self.color_out_linear(h), sigma], dim=-1)
+
+    # -- tensor-core evaluation (csrc/adnerf_mlp_tc.cu) ---------------------------------------------------------------------------
+    def tc_supported(self):
+        return (self.hid_dim in (128, 256) and len(self.density_linears) == 8 and len(self.color_linears) == 3 and self.skip_layer_indices == [4]
+                and (self.pos_dim - 3) % 6 == 0 and (self.view_dim - 3) % 6 == 0 and self.pos_dim <= 63 and self.view_dim <= 63)
+
+    def _tc_handle(self):
+        """Packed fp16 weight images of this network (rebuilt when a parameter changes: keyed on data_ptr + version)."""
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if getattr(self, '_tc', None) is not None and self._tc_key == key:
+            return self._tc
+        self._tc_free()
+        d = GfAdnerfDesc()
+        keep = []
+
+        def dev(t):
+            t = t.detach().float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+        d.hid, d.cond_dim, d.pos_multires, d.view_multires = self.hid_dim, self.cond_dim, (self.pos_dim - 3) // 6, (self.view_dim - 3) // 6
+        for i, lin in enumerate(self.density_linears):
+            d.dens_w[i], d.dens_b[i] = dev(lin.weight), dev(lin.bias)
+        d.dens_out_w, d.dens_out_b = dev(self.density_out_linear.weight), dev(self.density_out_linear.bias)
+        for i, lin in enumerate(self.color_linears):
+            d.col_w[i], d.col_b[i] = dev(lin.weight), dev(lin.bias)
+        d.col_out_w, d.col_out_b = dev(self.color_out_linear.weight), dev(self.color_out_linear.bias)
+        h = ctypes.c_void_p()
+        check(_lib.lib().gf_adnerf_mlp_create(ctypes.byref(d), ctypes.byref(h), stream_ptr()), "gf_adnerf_mlp_create")
+        self._tc, self._tc_key = h, key
+        return h
+
+    def _tc_free(self):
+        if getattr(self, '_tc', None) is not None:
+            _lib.lib().gf_adnerf_mlp_destroy(self._tc)
+            self._tc = None
+
+    def __del__(self):
+        try:
+            self._tc_free()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def forward_tc(self, rays_o, rays_d, z_vals, viewdirs, cond):
+        """raw [R, S, 4] at the points rays_o + rays_d * z_vals: embeddings + the whole backbone in libgfrender (one frame's cond [cond_dim])."""
+        R, S = z_vals.shape
+        h = self._tc_handle()
+        dev = z_vals.device
+        raw = torch.empty(R, S, 4, dtype=torch.float32, device=dev)
+        need = _lib.lib().gf_adnerf_mlp_workspace_bytes(h, R * S)
+        ws = getattr(self, '_tc_ws', None)
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = self._tc_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        ro, rd, z, vd, c = _f32c(rays_o), _f32c(rays_d), _f32c(z_vals), _f32c(viewdirs), _f32c(cond).view(-1)
+        check(_lib.lib().gf_adnerf_mlp_forward(h, ptr(ro), ptr(rd), ptr(z), ptr(vd), ptr(c), R, S, ptr(raw), ptr(ws), need, stream_ptr()),
+              "gf_adnerf_mlp_forward")
+        return raw
 
     def forward_folded(self, pos_embed, cond, view_embed, S):
         """Same function for samples of R rays x S depths: pos_embed [R*S, pos_dim], cond [cond_dim] (one frame), view_embed [R, view_dim].
@@ -256,6 +322,8 @@ def _query(network_fn, rays_o, rays_d, z_vals, cond, viewdirs, fine, **kwargs):
     R, S = z_vals.shape
     if isinstance(network_fn, ADNeRF) and cond.dim() == 1 and viewdirs is not None:
         net = network_fn.model_fine if fine else network_fn.model_coarse
+        if net.tc_supported():
+            return net.forward_tc(rays_o, rays_d, z_vals, viewdirs, cond)
         L = network_fn.pos_embedder.num_freqs
         pe = torch.empty(R * S, network_fn.pos_embedder.out_dim, device=z_vals.device)
         check(_lib.lib().gf_adnerf_embed_points(ptr(rays_o), ptr(rays_d), ptr(z_vals), R, S, L, ptr(pe), pe.shape[1], stream_ptr()))

@@ -157,6 +157,35 @@ GF_API int gf_adnerf_raw2outputs(const float* raw, const float* z_vals, const fl
 GF_API int gf_adnerf_sample_pdf(const float* z_vals, const float* weights, const float* u, uint32_t R, uint32_t S,
                                 uint32_t N_importance, int merge, float* z_out, float* samples_out, gf_stream_t stream);
 
+/* ---- the AD-NeRF backbone on tensor cores (modules/nerfs/adnerf/backbone.py:82-135: NeRFBackbone, num_density_linears = 8,
+ *      skip_layer_indices = [4], num_color_linears = 3; weights in torch nn.Linear layout [out, in], row-major, fp32, DEVICE) ------------- */
+typedef struct GfAdnerfDesc {
+    uint32_t hid;                 /* hid_dim (128 or 256); colour head = hid / 2 */
+    uint32_t cond_dim;            /* audio / condition feature size (64) */
+    uint32_t pos_multires;        /* frequency bands of the position embedding (10 -> 63 columns) */
+    uint32_t view_multires;       /* frequency bands of the view embedding (4 -> 27 columns) */
+    const float* dens_w[8];       /* density_linears[i].weight: [hid, 63+cond] (i = 0), [hid, 63+cond+hid] (i = 5), else [hid, hid] */
+    const float* dens_b[8];
+    const float* dens_out_w;      /* density_out_linear.weight [1, hid] */
+    const float* dens_out_b;
+    const float* col_w[3];        /* color_linears[i].weight: [hid/2, hid+27] (i = 0), else [hid/2, hid/2] */
+    const float* col_b[3];
+    const float* col_out_w;       /* color_out_linear.weight [3, hid/2] */
+    const float* col_out_b;
+} GfAdnerfDesc;
+typedef struct GfAdnerfMlp GfAdnerfMlp;
+
+/* Packs the weights into fp16 tensor-core images (copies: the caller's tensors need not outlive the call). */
+GF_API int gf_adnerf_mlp_create(const GfAdnerfDesc* desc, GfAdnerfMlp** out, gf_stream_t stream);
+GF_API void gf_adnerf_mlp_destroy(GfAdnerfMlp* m);
+GF_API uint64_t gf_adnerf_mlp_workspace_bytes(const GfAdnerfMlp* m, uint32_t n_samples);
+/* raw[R,S,4] = (rgb logits, sigma) of the network at the points rays_o + rays_d * z_vals[R,S], viewdirs [R,3] (unit), cond [cond_dim]
+ * (one frame): volume_rendering.py:153-155 run_network + backbone.py:99-135, embeddings included.  workspace: caller-owned,
+ * 1024-byte aligned, gf_adnerf_mlp_workspace_bytes(m, R*S) bytes. */
+GF_API int gf_adnerf_mlp_forward(const GfAdnerfMlp* m, const float* rays_o, const float* rays_d, const float* z_vals,
+                                 const float* viewdirs, const float* cond, uint32_t R, uint32_t S, float* raw, void* workspace,
+                                 uint64_t workspace_bytes, gf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Fused frame renderer: replaces the eval branch of NeRFRenderer.render()
  * (modules/radnerfs/renderer.py:263-367) and RADNeRFTorso.render()

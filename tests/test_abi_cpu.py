@@ -68,8 +68,9 @@ def test_argument_validation_happens_before_any_launch():
 def test_ctypes_structs_match_the_header_layout(tmp_path):
     """sizeof / offsetof of every field of the three ABI structs, computed by gcc FROM include/gfrender.h, against the ctypes mirrors."""
     import subprocess
+    from geneface_b200.adnerf import GfAdnerfDesc
     from geneface_b200.renderer import GfFrame, GfModelDesc, GfOut
-    structs = {"GfOut": GfOut, "GfFrame": GfFrame, "GfModelDesc": GfModelDesc}
+    structs = {"GfOut": GfOut, "GfFrame": GfFrame, "GfModelDesc": GfModelDesc, "GfAdnerfDesc": GfAdnerfDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gfrender.h"', 'int main(void) {']
     for name, cls in structs.items():
         lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
