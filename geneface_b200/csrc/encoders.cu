@@ -14,6 +14,8 @@
 // (Q_l^m = d^m/dz^m P_l), which is what the reference's expanded polynomials
 // (shencoder.cu:43-121) are; results agree to a few ulp.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "gf_common.cuh"
@@ -258,6 +260,91 @@ __global__ void __launch_bounds__(256) k_grid_backward(const T* __restrict__ gra
     }
 }
 
+// K14, B200 form (fp32 or fp16 gradients, C == 2, D == 2 or 3): level-major grid (blockIdx.y = level), one thread per sample carrying both
+// channels, grid-stride over the samples.
+//   * SMALL DENSE LEVELS (table <= the CTA's shared-memory budget: 3-D levels 0-1 = 4,920 / 13,824 entries, 2-D levels 0-6 of the May
+//     configuration) are where the reference's global atomics collide hardest: every sample of the batch lands in a few thousand entries
+//     (level 0: ~800 updates per entry per step at 0.5 M samples).  Here `priv_ctas` CTAs per such level each accumulate their share of the
+//     samples into a PRIVATE shared-memory copy of the level (shared-memory reductions, no L2 round trip, no cross-SM contention) and flush
+//     only the touched entries with one 8-byte vector reduction each: <= priv_ctas * entries global reductions instead of 2^D * B.
+//   * the other levels keep one 8-byte vector reduction per corner (RED.E.ADD.F32x2 / .F16x2): their updates are spread over >= 32 K entries
+//     and are bound by L2 reduction throughput, not by contention.
+// The sum order differs from the reference's (which is itself non-deterministic: atomics); parity is checked against an fp64 re-accumulation.
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_grid_backward_b200(const T* __restrict__ grad, const float* __restrict__ inputs,
+                                                             const int* __restrict__ offsets, T* __restrict__ grad_grid_all, uint32_t B,
+                                                             uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
+                                                             uint32_t interp, uint32_t priv_ctas, uint32_t priv_entries) {
+    extern __shared__ float2 tab[];
+    const uint32_t level = blockIdx.y;
+    const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
+    const bool priv = hashmap_size <= priv_entries;
+    if (priv && blockIdx.x >= priv_ctas) return;
+    const uint32_t nctas = priv ? (priv_ctas < gridDim.x ? priv_ctas : gridDim.x) : gridDim.x;
+    T* grad_grid = grad_grid_all + (size_t)(uint32_t)offsets[level] * 2;
+    float scale; uint32_t resolution;
+    level_geometry(level, S, H, scale, resolution);
+    if (priv) {
+        for (uint32_t e = threadIdx.x; e < hashmap_size; e += blockDim.x) tab[e] = make_float2(0.f, 0.f);
+        __syncthreads();
+    }
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += nctas * blockDim.x) {
+        const float* in = inputs + (size_t)b * D;
+        float pos[D];
+        uint32_t pos_grid[D];
+        bool oob = false;
+        #pragma unroll
+        for (int d = 0; d < D; d++) {
+            const float x = in[d];
+            oob = oob || x < 0 || x > 1;
+            pos[d] = __fmaf_rn(x, scale, align_corners ? 0.0f : 0.5f);
+            pos_grid[d] = (uint32_t)floorf(pos[d]);
+            pos[d] = __fsub_rn(pos[d], (float)pos_grid[d]);
+            if (interp == 1) pos[d] = pos[d] * pos[d] * (3.0f - 2.0f * pos[d]);
+        }
+        if (oob) continue;                                  // gridencoder.cu:281-286: out-of-range inputs get no gradient
+        const T* g = grad + (size_t)level * B * 2 + (size_t)b * 2;
+        const float g0 = to_float(g[0]), g1 = to_float(g[1]);
+        #pragma unroll
+        for (int idx = 0; idx < (1 << D); idx++) {
+            float w = 1;
+            uint32_t pgl[D];
+            #pragma unroll
+            for (int d = 0; d < D; d++) {
+                if ((idx & (1 << d)) == 0) { w *= 1 - pos[d]; pgl[d] = pos_grid[d]; }
+                else { w *= pos[d]; pgl[d] = pos_grid[d] + 1; }
+            }
+            const uint32_t e = grid_index<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
+            if (priv) {
+                atomicAdd(&tab[e].x, w * g0);
+                atomicAdd(&tab[e].y, w * g1);
+            } else if constexpr (std::is_same<T, float>::value) {
+                atomicAdd(reinterpret_cast<float2*>(grad_grid + (size_t)e * 2), make_float2(w * g0, w * g1));
+            } else {
+                atomicAdd(reinterpret_cast<__half2*>(grad_grid + (size_t)e * 2), __floats2half2_rn(w * g0, w * g1));
+            }
+        }
+    }
+    if (priv) {
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < hashmap_size; e += blockDim.x) {
+            const float2 v = tab[e];
+            if (v.x != 0.f || v.y != 0.f) {
+                if constexpr (std::is_same<T, float>::value) atomicAdd(reinterpret_cast<float2*>(grad_grid + (size_t)e * 2), v);
+                else atomicAdd(reinterpret_cast<__half2*>(grad_grid + (size_t)e * 2), __floats2half2_rn(v.x, v.y));
+            }
+        }
+    }
+}
+
+constexpr uint32_t GRID_BWD_PRIV_ENTRIES = 13824;            // 3-D level 1 of the May configuration: 110,592 B of shared memory, 2 CTAs / SM
+
+// GF_GRID_BWD=legacy selects the reference-shaped kernel (one thread per sample x level x channel pair, every corner a global reduction): A/B runs
+static bool grid_bwd_legacy() {
+    static const int v = [] { const char* e = getenv("GF_GRID_BWD"); return (e && !strcmp(e, "legacy")) ? 1 : 0; }();
+    return v == 1;
+}
+
 // K15  gridencoder.cu:342-368
 template <typename T, int D, int C>
 __global__ void k_grid_input_backward(const T* __restrict__ grad, const T* __restrict__ dy_dx, T* __restrict__ grad_inputs, uint32_t B,
@@ -341,9 +428,33 @@ static int launch_grid_backward(const void* grad, const float* inputs, const int
                                 uint32_t H, const void* dy_dx, void* grad_inputs, uint32_t gridtype, bool ac, uint32_t interp,
                                 cudaStream_t st) {
     constexpr int N_C = C < 2 ? C : 2;
+    int rc;
+    if constexpr (C == 2 && (D == 2 || D == 3)) {
+        if (!grid_bwd_legacy()) {
+            static bool attr = false;
+            if (!attr) {
+                cudaFuncSetAttribute(k_grid_backward_b200<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GRID_BWD_PRIV_ENTRIES * sizeof(float2)));
+                attr = true;
+            }
+            // privatised levels: enough CTAs that each still sees >= 8 K samples (the flush costs one pass over the level's table)
+            uint32_t priv_ctas = B / 8192;
+            priv_ctas = priv_ctas < 1 ? 1 : (priv_ctas > 32 ? 32 : priv_ctas);
+            uint32_t gx = div_up(B, 256 * 4);
+            gx = gx < priv_ctas ? priv_ctas : (gx > 1024 ? 1024 : gx);
+            k_grid_backward_b200<T, D><<<dim3(gx, L, 1), 256, GRID_BWD_PRIV_ENTRIES * sizeof(float2), st>>>(
+                (const T*)grad, inputs, offsets, (T*)grad_emb, B, L, S, H, gridtype, ac, interp, priv_ctas, GRID_BWD_PRIV_ENTRIES);
+            rc = check_launch("grid_encode_backward(b200)");
+            if (rc) return rc;
+            if (dy_dx && grad_inputs) {
+                k_grid_input_backward<T, D, C><<<div_up(B * D, 256), 256, 0, st>>>((const T*)grad, (const T*)dy_dx, (T*)grad_inputs, B, L);
+                rc = check_launch("grid_encode_backward(inputs)");
+            }
+            return rc;
+        }
+    }
     const dim3 grid(div_up(B * C / N_C, 256), L, 1);
     k_grid_backward<T, D, C, N_C><<<grid, 256, 0, st>>>((const T*)grad, inputs, offsets, (T*)grad_emb, B, L, S, H, gridtype, ac, interp);
-    int rc = check_launch("grid_encode_backward");
+    rc = check_launch("grid_encode_backward");
     if (rc) return rc;
     if (dy_dx && grad_inputs) {
         k_grid_input_backward<T, D, C><<<div_up(B * D, 256), 256, 0, st>>>((const T*)grad, (const T*)dy_dx, (T*)grad_inputs, B, L);

@@ -226,12 +226,12 @@ class NeRFRenderer(nn.Module):
         self.invalidate_fused()
         return super()._apply(fn, *a, **k)
 
-    def gf_model(self, check=True):
-        """Build (or reuse) the packed GfModel for the current weights.  check=True walks every parameter / buffer
-        (data_ptr, version) to detect in-place updates (~0.2 ms of host time); the sequence / graph paths pass check=False
+    def gf_model(self, verify=True):
+        """Build (or reuse) the packed GfModel for the current weights.  verify=True walks every parameter / buffer
+        (data_ptr, version) to detect in-place updates (~0.2 ms of host time); the sequence / graph paths pass verify=False
         and rely on invalidate_fused()."""
         _lib.require_cuda()
-        if self._gf_model is not None and self._gf_key is not None and not check:
+        if self._gf_model is not None and self._gf_key is not None and not verify:
             return self._gf_model
         key = self._tensors_key()
         if self._gf_model is not None and key == self._gf_key:
@@ -287,7 +287,7 @@ class NeRFRenderer(nn.Module):
         """One `gf_render_frame` call.  Rays come from rays_o/rays_d [N,3], or from pose [3|4,4] + intrinsics (by value), or from
         `dyn` = DEVICE float[22] (pose[12] | intrinsics[4] | torso_pose[6]) read at execution time -- the CUDA-graph form: no host
         conversion, nothing frame-specific in the launch arguments.  Returns dict of tensors."""
-        model = self.gf_model(check=check_weights)
+        model = self.gf_model(verify=check_weights)
         dev = cond_feat.device
         N = H * W
         fr = GfFrame()
