@@ -15,29 +15,40 @@ def partition_frames(num_frames, world_size, rank):
     return start, end
 
 
-def broadcast_model_(model, src=0):
-    """One flat broadcast of every parameter and buffer (4.34 M params + bitfield + torso grid ~ 17.7 MB)."""
+INFERENCE_SKIP = ('density_grid', 'step_counter')      # training-only state (the marcher reads density_bitfield, never density_grid)
+
+
+def broadcast_model_(model, src=0, inference_only=True):
+    """ONE broadcast of ONE packed byte blob from rank `src`: every parameter and buffer (any dtype, viewed as bytes, 16-byte aligned
+    slots) plus the python-side scalar `mean_density_torso` -- 4.34 M parameters + bitfield + torso grid = 17.7 MB for the May model.
+    inference_only (default) leaves out the training-only buffers `density_grid` (C x 128^3 fp32 = 8-25 MB) and `step_counter`.
+    Replaces "every rank torch.load()s the checkpoint" (base_nerf_infer.py:142).  Returns the number of bytes broadcast."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return 0
-    tensors = [p.data for p in model.parameters()] + [b.data for b in model.buffers()]
-    total = 0
-    by_dtype = {}
-    for t in tensors:
-        by_dtype.setdefault(t.dtype, []).append(t)
-    for dtype, ts in by_dtype.items():
-        flat = torch.cat([t.reshape(-1) for t in ts])
-        dist.broadcast(flat, src=src)
-        total += flat.numel() * flat.element_size()
-        off = 0
-        for t in ts:
-            n = t.numel()
-            t.copy_(flat[off:off + n].view_as(t))
-            off += n
-    extra = torch.tensor([float(getattr(model, 'mean_density_torso', 0.0))], device=tensors[0].device)
-    dist.broadcast(extra, src=src)
-    if hasattr(model, 'mean_density_torso'):
-        model.mean_density_torso = float(extra.item())
-    model.invalidate_fused()
+    named = [(n, p.data) for n, p in model.named_parameters()] + [(n, b.data) for n, b in model.named_buffers()]
+    if inference_only:
+        named = [(n, t) for n, t in named if n.split('.')[-1] not in INFERENCE_SKIP]
+    dev = named[0][1].device
+    offs, total = [], 0
+    for _, t in named:
+        offs.append(total)
+        total += (t.numel() * t.element_size() + 15) // 16 * 16
+    total += 16                                                      # trailing slot: mean_density_torso as float64
+    blob = torch.empty(total, dtype=torch.uint8, device=dev)
+    if dist.get_rank() == src:
+        for (_, t), o in zip(named, offs):
+            nb = t.numel() * t.element_size()
+            blob[o:o + nb].copy_(t.contiguous().view(-1).view(torch.uint8))
+        blob[total - 16:total - 8].copy_(torch.tensor([float(getattr(model, 'mean_density_torso', 0.0))], dtype=torch.float64, device=dev).view(torch.uint8))
+    dist.broadcast(blob, src=src)
+    if dist.get_rank() != src:
+        for (_, t), o in zip(named, offs):
+            nb = t.numel() * t.element_size()
+            t.copy_(blob[o:o + nb].view(t.dtype).view_as(t))
+        if hasattr(model, 'mean_density_torso'):
+            model.mean_density_torso = float(blob[total - 16:total - 8].view(torch.float64).item())
+    if hasattr(model, 'invalidate_fused'):
+        model.invalidate_fused()
     return total
 
 
