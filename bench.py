@@ -691,7 +691,9 @@ def run_train(args, rank, world, local):
         return
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     import bench_train
-    print(json.dumps(bench_train.run(steps=args.steps, warmup=args.warmup, local=local)), flush=True)
+    line = bench_train.run(steps=args.steps, warmup=args.warmup, local=local)
+    line["amp"] = bench_train.run(steps=args.steps, warmup=args.warmup, local=local, amp=True)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -270,6 +270,21 @@ __global__ void __launch_bounds__(256) k_grid_backward(const T* __restrict__ gra
 //   * the other levels keep one 8-byte vector reduction per corner (RED.E.ADD.F32x2 / .F16x2): their updates are spread over >= 32 K entries
 //     and are bound by L2 reduction throughput, not by contention.
 // The sum order differs from the reference's (which is itself non-deterministic: atomics); parity is checked against an fp64 re-accumulation.
+// One (entry, gradient pair) update.  When EVERY lane of a full warp targets the same entry -- samples of one ray inside one coarse cell, or
+// ambient coordinates clustered in a few cells of the 2-D grid: the dominant pattern behind the measured contention -- the warp tree-reduces
+// the 32 contributions with shuffles and commits once instead of serialising 32 same-address reductions.
+template <typename Commit>
+__device__ __forceinline__ void grid_update(uint32_t e, float a, float b, Commit&& commit) {
+    const uint32_t active = __activemask();
+    if (active == 0xffffffffu && __match_any_sync(0xffffffffu, e) == 0xffffffffu) {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if ((threadIdx.x & 31) == 0) commit(e, a, b);
+    } else {
+        commit(e, a, b);
+    }
+}
+
 template <typename T, int D>
 __global__ void __launch_bounds__(256) k_grid_backward_b200(const T* __restrict__ grad, const float* __restrict__ inputs,
                                                              const int* __restrict__ offsets, T* __restrict__ grad_grid_all, uint32_t B,
@@ -316,12 +331,11 @@ __global__ void __launch_bounds__(256) k_grid_backward_b200(const T* __restrict_
             }
             const uint32_t e = grid_index<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
             if (priv) {
-                atomicAdd(&tab[e].x, w * g0);
-                atomicAdd(&tab[e].y, w * g1);
+                grid_update(e, w * g0, w * g1, [&](uint32_t ee, float a, float b) { atomicAdd(&tab[ee].x, a); atomicAdd(&tab[ee].y, b); });
             } else if constexpr (std::is_same<T, float>::value) {
-                atomicAdd(reinterpret_cast<float2*>(grad_grid + (size_t)e * 2), make_float2(w * g0, w * g1));
+                grid_update(e, w * g0, w * g1, [&](uint32_t ee, float a, float b) { atomicAdd(reinterpret_cast<float2*>(grad_grid + (size_t)ee * 2), make_float2(a, b)); });
             } else {
-                atomicAdd(reinterpret_cast<__half2*>(grad_grid + (size_t)e * 2), __floats2half2_rn(w * g0, w * g1));
+                grid_update(e, w * g0, w * g1, [&](uint32_t ee, float a, float b) { atomicAdd(reinterpret_cast<__half2*>(grad_grid + (size_t)ee * 2), __floats2half2_rn(a, b)); });
             }
         }
     }

@@ -19,12 +19,13 @@ def main():
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--amp", action="store_true", help="fp16 autocast + GradScaler on both arms (the reference trains with amp: true)")
     args = ap.parse_args()
-    print(json.dumps(run(args.steps, args.warmup, 0, args.rays)), flush=True)
+    print(json.dumps(run(args.steps, args.warmup, 0, args.rays, args.amp)), flush=True)
 
 
-def run(steps=20, warmup=5, local=0, rays=4096):
-    args = argparse.Namespace(steps=steps, warmup=warmup, rays=rays)
+def run(steps=20, warmup=5, local=0, rays=4096, amp=False):
+    args = argparse.Namespace(steps=steps, warmup=warmup, rays=rays, amp=amp)
     import torch
     from geneface_b200 import synthetic, utils
     assert torch.cuda.is_available(), "needs a GPU"
@@ -42,14 +43,18 @@ def run(steps=20, warmup=5, local=0, rays=4096):
     target = torch.rand(1, args.rays, 3, device=dev, generator=g)
     bg_color = fi['bg_color'][:, inds]
 
+    scaler = torch.amp.GradScaler('cuda', enabled=args.amp)
+
     def step():
         torch.manual_seed(4)                                   # perturb noise
         opt.zero_grad(set_to_none=True)
-        out = model.render(rays_o, rays_d, fi['cond'], bgc, fi['poses6'], index=0, dt_gamma=hp['dt_gamma'], bg_color=bg_color, perturb=True,
-                           force_all_rays=False, max_steps=hp['max_steps'])
-        loss = ((out['rgb_map'] - target) ** 2).mean()
-        loss.backward()
-        opt.step()
+        with torch.autocast('cuda', dtype=torch.float16, enabled=args.amp):
+            out = model.render(rays_o, rays_d, fi['cond'], bgc, fi['poses6'], index=0, dt_gamma=hp['dt_gamma'], bg_color=bg_color, perturb=True,
+                               force_all_rays=False, max_steps=hp['max_steps'])
+            loss = ((out['rgb_map'].float() - target) ** 2).mean()
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
         return loss
 
     step()
@@ -75,7 +80,7 @@ def run(steps=20, warmup=5, local=0, rays=4096):
     rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:12]
     tot = sum(r.device_time_total for r in prof.key_averages()) or 1.0
     ref_line = reference_train_step(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args)
-    line = {"metric": "train step, %d rays (march_rays_train + field + composite + backward + Adam)" % args.rays, "ms_per_step": ms,
+    line = {"metric": "train step, %d rays (march_rays_train + field + composite + backward + Adam)" % args.rays, "ms_per_step": ms, "amp": bool(args.amp),
             "reference_cuda": ref_line, "mean_count": int(model.mean_count), "grid_backward": os.environ.get("GF_GRID_BWD", "b200 (privatised small levels)"),
             "rays_per_s": args.rays / (ms / 1000.0), "loss": float(loss), "grads_finite": bool(all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)),
             "top_kernels": [{"name": r.key[:70], "share": r.device_time_total / tot, "calls": r.count} for r in rows]}
@@ -94,15 +99,18 @@ def reference_train_step(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, a
         ref.train()
         ref.mean_count = int(model.mean_count)
         opt = torch.optim.Adam([p for p in ref.parameters() if p.requires_grad], lr=1e-3)
+        scaler = torch.amp.GradScaler('cuda', enabled=args.amp)
 
         def step():
             torch.manual_seed(4)
             opt.zero_grad(set_to_none=True)
-            out = ref.render(rays_o, rays_d, fi['cond'], bgc, fi['poses6'], index=0, dt_gamma=hp['dt_gamma'], bg_color=bg_color, perturb=True,
-                             force_all_rays=False, max_steps=hp['max_steps'])
-            loss = ((out['rgb_map'] - target) ** 2).mean()
-            loss.backward()
-            opt.step()
+            with torch.autocast('cuda', dtype=torch.float16, enabled=args.amp):
+                out = ref.render(rays_o, rays_d, fi['cond'], bgc, fi['poses6'], index=0, dt_gamma=hp['dt_gamma'], bg_color=bg_color, perturb=True,
+                                 force_all_rays=False, max_steps=hp['max_steps'])
+                loss = ((out['rgb_map'].float() - target) ** 2).mean()
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
             return loss
         for _ in range(args.warmup):
             step()

@@ -7,7 +7,8 @@ T=${1:-r02}
 CMD="python bench.py --steps 2 --warmup 3 --precision fp16 --no-cpu-baseline --no-ref-cuda --no-may --eager"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_$T.csv $CMD > gpurun_out/ncu_list_$T.log 2>&1
 echo "launch list rc=$?"; tail -2 gpurun_out/ncu_list_$T.log
-# the third warm-up frame's first round: k_tc_amb + k_tc_sigcol over 8,388,608 samples (10 k_tc_* launches per frame: 4 rounds + the empty extra round)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tc_ -s 20 -c 2 -f -o gpurun_out/prof_$T $CMD > gpurun_out/ncu_full_$T.log 2>&1
+# four consecutive k_tc_* launches inside the warm-up frames (10 per frame: 4 full rounds of 8,388,608 samples + the empty extra round);
+# scripts/ncu_field_json.py keeps the longest launch of each kernel = one full round
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tc_ -s 20 -c 4 -f -o gpurun_out/prof_$T $CMD > gpurun_out/ncu_full_$T.log 2>&1
 echo "full capture rc=$?"; tail -2 gpurun_out/ncu_full_$T.log; ls -la gpurun_out/*.ncu-rep
 python scripts/ncu_field_json.py gpurun_out/prof_$T.ncu-rep gpurun_out/field_ncu_$T.json

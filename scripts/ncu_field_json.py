@@ -45,7 +45,13 @@ def main(rep, out):
                 v = float(r[col[metric]].replace(",", ""))
                 k[name] = v * SCALE.get(units[col[metric]], 1.0)
         kernels.append(k)
-    field = [k for k in kernels if "k_tc_amb" in k["kernel"] or "k_tc_sigcol" in k["kernel"]]
+    # one FULL round per field kernel: the capture window may also contain the (empty) extra-round launches -> keep the longest launch of each
+    field = []
+    for name in ("k_tc_amb", "k_tc_sigcol"):
+        cand = [k for k in kernels if name in k["kernel"]]
+        if cand:
+            field.append(max(cand, key=lambda k: k.get("duration", 0.0)))
+    kernels = field or kernels
     res = {"source": rep, "kernels": kernels,
            "dram_bytes_per_round": int(sum(k.get("dram_read", 0) + k.get("dram_write", 0) for k in field)) if field else None,
            "l2_bytes_per_round": int(sum(k.get("l2_bytes", 0) for k in field)) if field else None,

@@ -266,6 +266,52 @@ def test_grid_encoder(oracle_ops, D, gridtype, interp):
     assert_close((0.5 * out + o_b).cpu().numpy(), o_c.cpu().numpy(), rel=1e-4, abs_=1e-5, what="linearity")
 
 
+@pytest.mark.parametrize("mode", ["priv", "legacy"])
+@pytest.mark.parametrize("D", [2, 3])
+def test_grid_backward_kernels_and_fp16_path(oracle_ops, D, mode):
+    """Hash-grid backward in both kernel forms -- `priv`: shared-memory privatised small levels + vector
+    reductions (forced here; by default chosen for batches >= 131,072 samples), `legacy`: one vector reduction per corner -- against the
+    oracle's fp64 re-accumulation of the same scatter, on a LARGE batch (the regime privatisation is for), in fp32 and through the
+    fp16 path (dtype = 1: half gradients, half2 reductions, as the reference runs under autocast, grid.py:43-44,65-89).
+    The mode is latched at first use per process, so each runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import numpy as np, torch, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})
+import scenes
+from geneface_b200 import _lib
+from oracle import cpu_ops
+cpu_ops.build()
+D = {D}
+offsets, S, emb = scenes.grid_setup(D, seed=20 + D)
+B, L, C = 200000, 16, 2
+x = scenes.unit_points(B, D, seed=30 + D)
+grad = (np.random.RandomState(40).randn(L, B, C) * 0.1).astype(np.float32)
+gg_ref, _ = cpu_ops.grid_encode_backward(grad, x, emb, offsets, S, 16, None, 1, False, 0)
+cu = lambda a, dt=None: (torch.from_numpy(np.ascontiguousarray(a)).cuda() if dt is None else torch.from_numpy(np.ascontiguousarray(a)).cuda().to(dt))
+xs, es, os_ = cu(x), cu(emb), cu(offsets)
+for dtype, tdt, rel in ((0, torch.float32, 1e-3), (1, torch.float16, 3e-2)):
+    g = cu(grad, tdt)
+    gg = torch.zeros(emb.shape, device='cuda', dtype=tdt)
+    _lib.check(_lib.lib().gf_grid_encode_backward(_lib.ptr(g), _lib.ptr(xs), _lib.ptr(es.to(tdt)), _lib.ptr(os_), _lib.ptr(gg), B, D, C, L,
+                                                  _lib.c_f32(S), 16, None, None, 1, 0, 0, dtype, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    got = gg.float().cpu().numpy()
+    scale = np.abs(gg_ref).max()
+    err = np.abs(got - gg_ref).max() / scale
+    print('dtype', dtype, 'max err / scale', err)
+    assert np.isfinite(got).all() and err < rel, (dtype, err)
+print('grid backward ok')
+"""
+    env = dict(os.environ, GF_GRID_BWD=mode)
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "grid backward ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    print(r.stdout.strip())
+
+
 def test_grid_encoder_module_autograd_and_tv():
     from geneface_b200.encoders import GridEncoder
     torch.manual_seed(0)
