@@ -368,7 +368,7 @@ def main():
     if headline:
         assert samples_per_frame == N * MAX_STEPS == 33554432, f"workload must evaluate 262144 x 128 samples, got {samples_per_frame}"
         assert s_total == MAX_STEPS and torso_px > 0
-    seq.render(poses_h, conds_h, bg, 0, min(args.warmup, 3), out_rgb8=host_ring)        # warm the e2e path too (graph capture, ring)
+    seq.render(poses_h, conds_h, bg, 0, min(args.warmup, 3, args.steps), out_rgb8=host_ring)        # warm the e2e path too (graph capture, ring)
 
     # ---- timed: resident inputs ----
     barrier()

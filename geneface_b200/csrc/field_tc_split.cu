@@ -47,23 +47,19 @@ constexpr uint32_t WB2_TOTAL = WB2_SH + 128 * 128;          // 106,496
 static_assert(WA_TOTAL == 81920 && WB2_TOTAL == 106496, "image sizes");
 static_assert(WB2_MRG % 1024 == 0 && WB2_COL1 % 1024 == 0 && WB2_SH % 1024 == 0, "1024-byte aligned blocks");
 
-// (experimental, -DGF_STAGE_L0=1) the north-star's "TMA staging of grid tiles" where it fits: kernel A has 38 KB of shared memory left
-// (+ the 12 KB view-direction ring it does not use), enough for the whole 3-D level 0 (17^3 = 4,913 entries, 39 KB): staged once per CTA
-// by cp.async.bulk next to the weights; the level's 8 corner loads per sample (of 100) are then served from shared memory.
-#ifndef GF_STAGE_L0
-#define GF_STAGE_L0 0
-#endif
-constexpr uint32_t SP_L0_MAX_BYTES = 40960;
+// Tried and removed (measured, profiles/r02_summary.md): staging the whole 3-D level 0 (4,913 entries, 39 KB) into kernel A's spare shared
+// memory with cp.async.bulk and serving its 8 corner loads per sample from there: 8.530 vs 8.536 ms/frame, l1tex hit rate 62.8 -> 54.5 %
+// (the level was L1-resident anyway; only the remaining, colder loads are left in the statistic), +0.7 % instructions.  The dense coarse
+// levels are not where the gathers cost: the producers are issue-bound, not L1-bound.
 
 // shared-memory layout (same skeleton for both kernels; W = weight image bytes)
 template <uint32_t W>
 struct SpSmem {
     static constexpr uint32_t F = W;
-    static constexpr uint32_t DIR = F + SP_NSLOT * SP_TILE_BYTES;    // per slot: 128 x float4 view directions (kernel B); kernel A + GF_STAGE_L0: 3-D level 0
-    static constexpr uint32_t DIR_BYTES = (GF_STAGE_L0 && W == 81920) ? 40960 : SP_NSLOT * 128 * 16;
-    static constexpr uint32_t BIAS = DIR + DIR_BYTES;                // 128 floats
-    static constexpr uint32_t BAR = BIAS + 512;                      // wbar, full[NSLOT], empty[NSLOT], mma[2]
-    static constexpr uint32_t TMEM = BAR + 8 * (1 + 2 * SP_NSLOT + 2);
+    static constexpr uint32_t DIR = F + SP_NSLOT * SP_TILE_BYTES;    // per slot: 128 x float4 view directions (kernel B)
+    static constexpr uint32_t BIAS = DIR + SP_NSLOT * 128 * 16;      // 128 floats
+    static constexpr uint32_t BAR = BIAS + 512;                      // wbar, full[NSLOT], empty[NSLOT], mma[2], mma_hi[2]
+    static constexpr uint32_t TMEM = BAR + 8 * (1 + 2 * SP_NSLOT + 4);
     static constexpr uint32_t TOTAL = TMEM + 16;
     static constexpr uint32_t BYTES = TOTAL + 1024;
 };
@@ -124,7 +120,6 @@ struct SpArgs {
     const uint8_t* wimg;
     const float* bias;          // A: per-frame cond bias [128]; B: individual-code bias [128] or null
     float w_amb2[256];          // A only
-    uint32_t l0_bytes;          // A only, GF_STAGE_L0: bytes of 3-D level 0 to stage (0: level too large / hashed)
     FieldTcIO io;
     float* dbg;
 };
@@ -143,6 +138,8 @@ __device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, cons
         }
         mbar_init(sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT), 1);
         mbar_init(sbase + L::BAR + 8 * (2 + 2 * SP_NSLOT), 1);
+        mbar_init(sbase + L::BAR + 8 * (3 + 2 * SP_NSLOT), 1);           // second commit group of a stream (upper accumulator half)
+        mbar_init(sbase + L::BAR + 8 * (4 + 2 * SP_NSLOT), 1);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(sbase + L::TMEM, 512);
@@ -151,10 +148,8 @@ __device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, cons
     __syncthreads();
     tc_fence_after();
     if (tid == 0) {
-        const uint32_t extra = (GF_STAGE_L0 && W == WA_TOTAL) ? a.l0_bytes : 0;
-        mbar_expect_tx(sbase + L::BAR, W + extra);
+        mbar_expect_tx(sbase + L::BAR, W);
         for (int i = 0; i < ncuts; i++) bulk_g2s(sbase + cuts[i], a.wimg + cuts[i], cuts[i + 1] - cuts[i], sbase + L::BAR);
-        if (extra) bulk_g2s(sbase + L::DIR, a.grid.lbase[0], extra, sbase + L::BAR);     // kernel A: level 0 over the (unused) direction ring + spare
     }
     mbar_wait(sbase + L::BAR, 0);
     return *reinterpret_cast<uint32_t*>(smem + L::TMEM);
@@ -174,7 +169,7 @@ __device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, cons
 // reference's corner-order sum by rounding only; it is rounded to fp16 right after).
 // ALLFLAT: every level of the batch drops z and is not hashed -> only the 4 corners of the z0 plane exist (uniform fast path).
 template <bool ALLFLAT>
-__device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x, float y, float z, float2 (&out)[4], const float2* l0_smem = nullptr) {
+__device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x, float y, float z, float2 (&out)[4]) {
     float fx[4], fy[4], fz[4];
     float2 v[4][8];
     #pragma unroll
@@ -186,13 +181,7 @@ __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x,
         px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy); pz = __fsub_rn(pz, (float)gz);
         if (g.interp == 1) { px = smooth_(px); py = smooth_(py); pz = smooth_(pz); }
         fx[i] = px; fy[i] = py; fz[i] = pz;
-#if GF_STAGE_L0
-        const float2* tab = (!ALLFLAT && l == 0 && l0_smem) ? l0_smem : g.lbase[l];      // generic loads: level 0 may live in shared memory
-#define GF_LD3(p) (*(p))
-#else
         const float2* __restrict__ tab = g.lbase[l];
-#define GF_LD3(p) __ldg(p)
-#endif
         const uint32_t mask = g.lv.mask[l], sy = g.lv.sy[l], sz = g.lv.sz[l];
         const bool hashed = !ALLFLAT && g.lv.hashed[l] != 0;
         const bool has_z = !ALLFLAT && (hashed || sz != 0);
@@ -211,10 +200,10 @@ __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x,
             idx[4] = b + sz; idx[5] = b + sz + 1; idx[6] = b + sz + sy; idx[7] = b + sz + sy + 1;
         }
         #pragma unroll
-        for (int c = 0; c < 4; c++) v[i][c] = GF_LD3(tab + (idx[c] & mask));
+        for (int c = 0; c < 4; c++) v[i][c] = __ldg(tab + (idx[c] & mask));
         if (!ALLFLAT) {
             #pragma unroll
-            for (int c = 4; c < 8; c++) v[i][c] = has_z ? GF_LD3(tab + (idx[c] & mask)) : make_float2(0.f, 0.f);
+            for (int c = 4; c < 8; c++) v[i][c] = has_z ? __ldg(tab + (idx[c] & mask)) : make_float2(0.f, 0.f);
             if (!has_z) fz[i] = 0.f;
         }
     }
@@ -297,16 +286,25 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             for (int q = 0; q < 4; q++) flat = flat && a.grid.lv.sz[4 * u + q] == 0 && a.grid.lv.hashed[4 * u + q] == 0;
             flat_units |= (flat ? 1u : 0u) << u;
         }
+        // the row's position is fetched ONE TILE AHEAD: its DRAM latency (~10 % of this kernel's stall samples when loaded at the top of
+        // the tile, profiles/r02_summary.md) overlaps the previous tile's gathers
+        auto fetch_pos = [&](uint32_t j) {
+            float3 p = make_float3(0.f, 0.f, 0.f);
+            const uint32_t i = (blockIdx.x + j * gridDim.x) * 128 + row;
+            if (j < my_tiles && i < M) {
+                if (a.io.pos4) { const float4 q = a.io.pos4[i]; p = make_float3(q.x, q.y, q.z); }
+                else p = make_float3(a.io.xyzs[3 * (size_t)i], a.io.xyzs[3 * (size_t)i + 1], a.io.xyzs[3 * (size_t)i + 2]);
+            }
+            return p;
+        };
+        float3 nxt = fetch_pos(0);
         #pragma unroll 1
         for (uint32_t j = 0; j < my_tiles; j++) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
             const uint32_t i = tile * 128 + row;
             const bool valid = i < M;
-            float x = 0.f, y = 0.f, z = 0.f;
-            if (valid) {
-                if (a.io.pos4) { const float4 p = a.io.pos4[i]; x = p.x; y = p.y; z = p.z; }
-                else { x = a.io.xyzs[3 * (size_t)i]; y = a.io.xyzs[3 * (size_t)i + 1]; z = a.io.xyzs[3 * (size_t)i + 2]; }
-            }
+            const float x = nxt.x, y = nxt.y, z = nxt.z;
+            nxt = fetch_pos(j + 1);
             float ux = (x + a.bound) * a.inv2b, uy = (y + a.bound) * a.inv2b, uz = (z + a.bound) * a.inv2b;
             // out-of-range inputs encode to 0 (gridencoder.cu:110-135): sample the centre, zero the result
             const bool oob = ux < 0 || ux > 1 || uy < 0 || uy > 1 || uz < 0 || uz > 1;
@@ -320,7 +318,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
                 const uint32_t u = half + 2 * b;
                 float2 f[4];
                 if ((flat_units >> u) & 1) gather3_dyn4<true>(a.grid, 4 * u, ux, uy, uz, f);
-                else gather3_dyn4<false>(a.grid, 4 * u, ux, uy, uz, f, (GF_STAGE_L0 && a.l0_bytes) ? reinterpret_cast<const float2*>(smem + L::DIR) : nullptr);
+                else gather3_dyn4<false>(a.grid, 4 * u, ux, uy, uz, f);
                 if (oob) { f[0] = f[1] = f[2] = f[3] = make_float2(0.f, 0.f); }
                 const uint4 hi = make_uint4(pack_h2(f[0].x, f[0].y), pack_h2(f[1].x, f[1].y), pack_h2(f[2].x, f[2].y), pack_h2(f[3].x, f[3].y));
                 *reinterpret_cast<uint4*>(F + sw128(row, u)) = hi;
@@ -338,9 +336,10 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
         const uint32_t t_d = tmem_base + (((warp & 3) * 32) << 16) + stream * SP_TM_STREAM;
         const uint32_t m_d = tmem_base + stream * SP_TM_STREAM;
         const uint32_t bar_mma = sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT + stream);
+        const uint32_t bar_mma_hi = sbase + L::BAR + 8 * (3 + 2 * SP_NSLOT + stream);
         const uint32_t w_addr = sbase;
         const bool leader = row == 0;
-        uint32_t phase = 0;
+        uint32_t phase = 0, phase_hi = 0;
         for (uint32_t j = stream; j < my_tiles; j += 2) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
             const uint32_t i = tile * 128 + row;
@@ -366,18 +365,26 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             epilogue_relu_to_A_n<true, 4>(t_d, t_d + SP_TM_AHI, t_d + SP_TM_ALO, 0, bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);
             tc_fence_before();
             bar_named(1 + stream, 128);
+            // The layer (24 MMAs, ~1,500 tensor-pipe clocks: the longest stretch this stream would otherwise spend spinning on one
+            // mbarrier) is issued as TWO 64-column halves with their own commits: the fp32 output layer below starts on accumulator
+            // columns 0..63 while the tensor pipe is still producing columns 64..127.  Rows 64..127 of a weight chunk start 64 x 128 B
+            // into it (whole 8-row swizzle atoms), so the second half only offsets the B descriptors and the accumulator column.
             if (leader) {
                 tc_fence_after();
                 #pragma unroll
-                for (int k = 0; k < 8; k++)
-                    mma_ts(m_d, m_d + SP_TM_AHI + 8 * k, smem_desc(w_addr + WA_A1H + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), k);
-                #pragma unroll
-                for (int k = 0; k < 8; k++)
-                    mma_ts(m_d, m_d + SP_TM_ALO + 8 * k, smem_desc(w_addr + WA_A1H + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), 1);
-                #pragma unroll
-                for (int k = 0; k < 8; k++)
-                    mma_ts(m_d, m_d + SP_TM_AHI + 8 * k, smem_desc(w_addr + WA_A1L + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), 1);
-                mma_commit(bar_mma);
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t dd = m_d + 64 * h, wo = h * (64 * 128);
+                    #pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        mma_ts(dd, m_d + SP_TM_AHI + 8 * k, smem_desc(w_addr + WA_A1H + wo + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(64), k);
+                    #pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        mma_ts(dd, m_d + SP_TM_ALO + 8 * k, smem_desc(w_addr + WA_A1H + wo + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(64), 1);
+                    #pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        mma_ts(dd, m_d + SP_TM_AHI + 8 * k, smem_desc(w_addr + WA_A1L + wo + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(64), 1);
+                    mma_commit(h ? bar_mma_hi : bar_mma);
+                }
             }
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
@@ -385,6 +392,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;          // (even, odd) column partial sums of the two outputs
             #pragma unroll 1
             for (int c = 0; c < 4; c++) {
+                if (c == 2) { stream_wait_mma(bar_mma_hi, phase_hi); tc_fence_after(); }
                 float v[32];
                 tmem_ld32(t_d + 32 * c, v);
                 if (dbg) {
@@ -481,10 +489,11 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
         const uint32_t m_d = tmem_base + stream * SP_TM_STREAM;
         const uint32_t t_a = t_d + SP_TM_A, m_a = m_d + SP_TM_A;
         const uint32_t bar_mma = sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT + stream);
+        const uint32_t bar_mma_hi = sbase + L::BAR + 8 * (3 + 2 * SP_NSLOT + stream);     // commit of the upper accumulator half of a split layer
         const uint32_t w_addr = sbase;
         const bool leader = row == 0;
         const bool sigma_only = !a.io.out4 && !a.io.rgbs;          // density query (uniform)
-        uint32_t phase = 0;
+        uint32_t phase = 0, phase_hi = 0;
         for (uint32_t j = stream; j < my_tiles; j += 2) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
             const uint32_t i = tile * 128 + row;
@@ -508,12 +517,17 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             tc_fence_before();
             bar_named(1 + stream, 128);
             // ---- sigma layer 1 -----------------------------------------------------------------------------------------
+            //      issued as two 64-column halves with their own commits (see k_tc_amb): the epilogue converts columns 0..63 while the
+            //      tensor pipe still produces 64..127
             if (leader) {
                 tc_fence_after();
                 #pragma unroll
-                for (int k = 0; k < 8; k++)
-                    mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_SIG1 + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), k);
-                mma_commit(bar_mma);
+                for (int h = 0; h < 2; h++) {
+                    #pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        mma_ts(m_d + 64 * h, m_a + 8 * k, smem_desc(w_addr + WB2_SIG1 + h * (64 * 128) + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(64), k);
+                    mma_commit(h ? bar_mma_hi : bar_mma);
+                }
             }
             // SH(dir) -> F[row][k 32..47]: the sigma-layer-0 MMA that read this slot has completed (waited above)
             {
@@ -529,7 +543,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             }
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
-            epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 4 * 128 * 144 : nullptr);
+            epilogue_relu_to_A_pipe_halves<false>(t_d, t_a, nullptr, dbg ? dbg + 4 * 128 * 144 : nullptr, bar_mma_hi, phase_hi);
             tc_fence_before();
             bar_named(1 + stream, 128);
             if (sigma_only) {
@@ -553,22 +567,31 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                 continue;
             }
             // ---- merged sigma layer 2 x colour layer 0 (N = 144) + SH part (SS, K = 16, N = 128) --------------------------
+            //      two halves again: columns 0..63, then 64..143 (colour columns 64..127 + the sigma-logit block 128..143)
             if (leader) {
                 tc_fence_after();
                 #pragma unroll
-                for (int k = 0; k < 8; k++)
-                    mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_MRG + (k >> 2) * (144 * 128) + 32 * (k & 3)), idesc_f16(144), k);
-                mma_ss(m_d, smem_desc(f_addr + 64), smem_desc(w_addr + WB2_SH), idesc_f16(128), 1);
-                mma_commit(bar_mma);
+                for (int h = 0; h < 2; h++) {
+                    #pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        mma_ts(m_d + 64 * h, m_a + 8 * k, smem_desc(w_addr + WB2_MRG + h * (64 * 128) + (k >> 2) * (144 * 128) + 32 * (k & 3)), idesc_f16(h ? 80 : 64), k);
+                    mma_ss(m_d + 64 * h, smem_desc(f_addr + 64), smem_desc(w_addr + WB2_SH + h * (64 * 128)), idesc_f16(64), 1);
+                    mma_commit(h ? bar_mma_hi : bar_mma);
+                }
             }
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
-            if (leader) mbar_arrive(bar_empty + 8 * slot);                // last reader of the feature tile is done
             float sg[4];
+            {
+                // the epilogue's wait on bar_mma_hi also covers the sigma column and the last read of the feature tile
+                uint32_t ph = phase_hi;
+                if (a.bias) epilogue_relu_to_A_pipe_halves<true>(t_d, t_a, bias_ind, dbg ? dbg + 5 * 128 * 144 : nullptr, bar_mma_hi, ph);
+                else epilogue_relu_to_A_pipe_halves<false>(t_d, t_a, nullptr, dbg ? dbg + 5 * 128 * 144 : nullptr, bar_mma_hi, ph);
+                phase_hi = ph;
+            }
+            if (leader) mbar_arrive(bar_empty + 8 * slot);                // last reader of the feature tile is done
             tmem_ld4(t_d + 128, sg);
             if (dbg) dbg[5 * 128 * 144 + 128] = sg[0];
-            if (a.bias) epilogue_relu_to_A_pipe<true>(t_d, t_a, bias_ind, dbg ? dbg + 5 * 128 * 144 : nullptr);
-            else epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 5 * 128 * 144 : nullptr);
             tc_fence_before();
             bar_named(1 + stream, 128);
             // ---- colour layer 1 (N = 16; 3 real outputs) -> sigmoid ---------------------------------------------------------
@@ -700,10 +723,6 @@ int field_tc_launch(const GfModel* model, const FieldTcIO& io_in, cudaStream_t s
     a.io = io;
     a.dbg = model->tc_dbg;
     a.grid = model->dev.pos;
-    {   // GF_STAGE_L0: 3-D level 0 if it is dense (not hashed), fits, and is a whole number of 16-byte units
-        const uint32_t bytes = model->dev.pos.lv.hsize[0] * 8;
-        a.l0_bytes = (model->dev.pos.lv.hashed[0] == 0 && bytes <= SP_L0_MAX_BYTES && bytes % 16 == 0) ? bytes : 0;
-    }
     a.wimg = (const uint8_t*)model->tc2_blob;
     a.bias = io.bias_amb;
     memcpy(a.w_amb2, model->w_amb2_host, sizeof(a.w_amb2));
