@@ -58,8 +58,8 @@ struct SpSmem {
     static constexpr uint32_t F = W;
     static constexpr uint32_t DIR = F + SP_NSLOT * SP_TILE_BYTES;    // per slot: 128 x float4 view directions (kernel B)
     static constexpr uint32_t BIAS = DIR + SP_NSLOT * 128 * 16;      // 128 floats
-    static constexpr uint32_t BAR = BIAS + 512;                      // wbar, full[NSLOT], empty[NSLOT], mma[2], mma_hi[2]
-    static constexpr uint32_t TMEM = BAR + 8 * (1 + 2 * SP_NSLOT + 4);
+    static constexpr uint32_t BAR = BIAS + 512;                      // wbar, full[NSLOT], empty[NSLOT], mma[2]
+    static constexpr uint32_t TMEM = BAR + 8 * (1 + 2 * SP_NSLOT + 2);
     static constexpr uint32_t TOTAL = TMEM + 16;
     static constexpr uint32_t BYTES = TOTAL + 1024;
 };
@@ -138,8 +138,6 @@ __device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, cons
         }
         mbar_init(sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT), 1);
         mbar_init(sbase + L::BAR + 8 * (2 + 2 * SP_NSLOT), 1);
-        mbar_init(sbase + L::BAR + 8 * (3 + 2 * SP_NSLOT), 1);           // second commit group of a stream (upper accumulator half)
-        mbar_init(sbase + L::BAR + 8 * (4 + 2 * SP_NSLOT), 1);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(sbase + L::TMEM, 512);
@@ -286,8 +284,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             for (int q = 0; q < 4; q++) flat = flat && a.grid.lv.sz[4 * u + q] == 0 && a.grid.lv.hashed[4 * u + q] == 0;
             flat_units |= (flat ? 1u : 0u) << u;
         }
-        // the row's position is fetched ONE TILE AHEAD: its DRAM latency (~10 % of this kernel's stall samples when loaded at the top of
-        // the tile, profiles/r02_summary.md) overlaps the previous tile's gathers
+        // the row's position is fetched ONE TILE AHEAD (as kernel B does with its inputs): ~10 % of this kernel's warp-stall samples sat on
+        // the position load at the top of the tile (profiles/r02_summary.md)
         auto fetch_pos = [&](uint32_t j) {
             float3 p = make_float3(0.f, 0.f, 0.f);
             const uint32_t i = (blockIdx.x + j * gridDim.x) * 128 + row;
@@ -336,10 +334,9 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
         const uint32_t t_d = tmem_base + (((warp & 3) * 32) << 16) + stream * SP_TM_STREAM;
         const uint32_t m_d = tmem_base + stream * SP_TM_STREAM;
         const uint32_t bar_mma = sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT + stream);
-        const uint32_t bar_mma_hi = sbase + L::BAR + 8 * (3 + 2 * SP_NSLOT + stream);
         const uint32_t w_addr = sbase;
         const bool leader = row == 0;
-        uint32_t phase = 0, phase_hi = 0;
+        uint32_t phase = 0;
         for (uint32_t j = stream; j < my_tiles; j += 2) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
             const uint32_t i = tile * 128 + row;
@@ -365,26 +362,18 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             epilogue_relu_to_A_n<true, 4>(t_d, t_d + SP_TM_AHI, t_d + SP_TM_ALO, 0, bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);
             tc_fence_before();
             bar_named(1 + stream, 128);
-            // The layer (24 MMAs, ~1,500 tensor-pipe clocks: the longest stretch this stream would otherwise spend spinning on one
-            // mbarrier) is issued as TWO 64-column halves with their own commits: the fp32 output layer below starts on accumulator
-            // columns 0..63 while the tensor pipe is still producing columns 64..127.  Rows 64..127 of a weight chunk start 64 x 128 B
-            // into it (whole 8-row swizzle atoms), so the second half only offsets the B descriptors and the accumulator column.
             if (leader) {
                 tc_fence_after();
                 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const uint32_t dd = m_d + 64 * h, wo = h * (64 * 128);
-                    #pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        mma_ts(dd, m_d + SP_TM_AHI + 8 * k, smem_desc(w_addr + WA_A1H + wo + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(64), k);
-                    #pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        mma_ts(dd, m_d + SP_TM_ALO + 8 * k, smem_desc(w_addr + WA_A1H + wo + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(64), 1);
-                    #pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        mma_ts(dd, m_d + SP_TM_AHI + 8 * k, smem_desc(w_addr + WA_A1L + wo + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(64), 1);
-                    mma_commit(h ? bar_mma_hi : bar_mma);
-                }
+                for (int k = 0; k < 8; k++)
+                    mma_ts(m_d, m_d + SP_TM_AHI + 8 * k, smem_desc(w_addr + WA_A1H + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), k);
+                #pragma unroll
+                for (int k = 0; k < 8; k++)
+                    mma_ts(m_d, m_d + SP_TM_ALO + 8 * k, smem_desc(w_addr + WA_A1H + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), 1);
+                #pragma unroll
+                for (int k = 0; k < 8; k++)
+                    mma_ts(m_d, m_d + SP_TM_AHI + 8 * k, smem_desc(w_addr + WA_A1L + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), 1);
+                mma_commit(bar_mma);
             }
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
@@ -392,7 +381,6 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;          // (even, odd) column partial sums of the two outputs
             #pragma unroll 1
             for (int c = 0; c < 4; c++) {
-                if (c == 2) { stream_wait_mma(bar_mma_hi, phase_hi); tc_fence_after(); }
                 float v[32];
                 tmem_ld32(t_d + 32 * c, v);
                 if (dbg) {
@@ -489,11 +477,10 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
         const uint32_t m_d = tmem_base + stream * SP_TM_STREAM;
         const uint32_t t_a = t_d + SP_TM_A, m_a = m_d + SP_TM_A;
         const uint32_t bar_mma = sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT + stream);
-        const uint32_t bar_mma_hi = sbase + L::BAR + 8 * (3 + 2 * SP_NSLOT + stream);     // commit of the upper accumulator half of a split layer
         const uint32_t w_addr = sbase;
         const bool leader = row == 0;
         const bool sigma_only = !a.io.out4 && !a.io.rgbs;          // density query (uniform)
-        uint32_t phase = 0, phase_hi = 0;
+        uint32_t phase = 0;
         for (uint32_t j = stream; j < my_tiles; j += 2) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
             const uint32_t i = tile * 128 + row;
@@ -517,17 +504,12 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             tc_fence_before();
             bar_named(1 + stream, 128);
             // ---- sigma layer 1 -----------------------------------------------------------------------------------------
-            //      issued as two 64-column halves with their own commits (see k_tc_amb): the epilogue converts columns 0..63 while the
-            //      tensor pipe still produces 64..127
             if (leader) {
                 tc_fence_after();
                 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    #pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        mma_ts(m_d + 64 * h, m_a + 8 * k, smem_desc(w_addr + WB2_SIG1 + h * (64 * 128) + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(64), k);
-                    mma_commit(h ? bar_mma_hi : bar_mma);
-                }
+                for (int k = 0; k < 8; k++)
+                    mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_SIG1 + (k >> 2) * (128 * 128) + 32 * (k & 3)), idesc_f16(128), k);
+                mma_commit(bar_mma);
             }
             // SH(dir) -> F[row][k 32..47]: the sigma-layer-0 MMA that read this slot has completed (waited above)
             {
@@ -543,7 +525,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             }
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
-            epilogue_relu_to_A_pipe_halves<false>(t_d, t_a, nullptr, dbg ? dbg + 4 * 128 * 144 : nullptr, bar_mma_hi, phase_hi);
+            epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 4 * 128 * 144 : nullptr);
             tc_fence_before();
             bar_named(1 + stream, 128);
             if (sigma_only) {
@@ -567,31 +549,22 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                 continue;
             }
             // ---- merged sigma layer 2 x colour layer 0 (N = 144) + SH part (SS, K = 16, N = 128) --------------------------
-            //      two halves again: columns 0..63, then 64..143 (colour columns 64..127 + the sigma-logit block 128..143)
             if (leader) {
                 tc_fence_after();
                 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    #pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        mma_ts(m_d + 64 * h, m_a + 8 * k, smem_desc(w_addr + WB2_MRG + h * (64 * 128) + (k >> 2) * (144 * 128) + 32 * (k & 3)), idesc_f16(h ? 80 : 64), k);
-                    mma_ss(m_d + 64 * h, smem_desc(f_addr + 64), smem_desc(w_addr + WB2_SH + h * (64 * 128)), idesc_f16(64), 1);
-                    mma_commit(h ? bar_mma_hi : bar_mma);
-                }
+                for (int k = 0; k < 8; k++)
+                    mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_MRG + (k >> 2) * (144 * 128) + 32 * (k & 3)), idesc_f16(144), k);
+                mma_ss(m_d, smem_desc(f_addr + 64), smem_desc(w_addr + WB2_SH), idesc_f16(128), 1);
+                mma_commit(bar_mma);
             }
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
-            float sg[4];
-            {
-                // the epilogue's wait on bar_mma_hi also covers the sigma column and the last read of the feature tile
-                uint32_t ph = phase_hi;
-                if (a.bias) epilogue_relu_to_A_pipe_halves<true>(t_d, t_a, bias_ind, dbg ? dbg + 5 * 128 * 144 : nullptr, bar_mma_hi, ph);
-                else epilogue_relu_to_A_pipe_halves<false>(t_d, t_a, nullptr, dbg ? dbg + 5 * 128 * 144 : nullptr, bar_mma_hi, ph);
-                phase_hi = ph;
-            }
             if (leader) mbar_arrive(bar_empty + 8 * slot);                // last reader of the feature tile is done
+            float sg[4];
             tmem_ld4(t_d + 128, sg);
             if (dbg) dbg[5 * 128 * 144 + 128] = sg[0];
+            if (a.bias) epilogue_relu_to_A_pipe<true>(t_d, t_a, bias_ind, dbg ? dbg + 5 * 128 * 144 : nullptr);
+            else epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 5 * 128 * 144 : nullptr);
             tc_fence_before();
             bar_named(1 + stream, 128);
             // ---- colour layer 1 (N = 16; 3 real outputs) -> sigmoid ---------------------------------------------------------

@@ -214,36 +214,6 @@ __device__ __forceinline__ void epilogue_relu_to_A_pipe(uint32_t t_d, uint32_t t
     tmem_wait_st();
 }
 
-// Same, for a layer whose MMAs were issued as two column halves with separate commits (`bar_hi` = the commit of columns 64..127): the
-// conversion of columns 0..63 runs while the tensor pipe is still producing the upper half; the wait sits right before the first load of it.
-template <bool BIAS>
-__device__ __forceinline__ void epilogue_relu_to_A_pipe_halves(uint32_t t_d, uint32_t t_a, const float* __restrict__ bias_smem, float* dbg,
-                                                               uint32_t bar_hi, uint32_t& phase_hi) {
-    uint32_t r[2][32];
-    tmem_ld32_issue(t_d, r[0]);
-    tmem_wait_ld32(r[0]);
-    #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        uint32_t (&cur)[32] = r[c & 1];
-        if (c == 1) { mbar_wait(bar_hi, phase_hi); phase_hi ^= 1; tc_fence_after(); }
-        if (c < 3) tmem_ld32_issue(t_d + 32 * (c + 1), r[(c + 1) & 1]);
-        if (dbg) {
-            #pragma unroll
-            for (int i = 0; i < 32; i++) dbg[32 * c + i] = __uint_as_float(cur[i]);
-        }
-        uint32_t p[16];
-        #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            float v0 = __uint_as_float(cur[2 * i]), v1 = __uint_as_float(cur[2 * i + 1]);
-            if (BIAS) { const float2 b = *reinterpret_cast<const float2*>(bias_smem + 32 * c + 2 * i); v0 += b.x; v1 += b.y; }
-            p[i] = pack_relu_h2(v0, v1);
-        }
-        tmem_st16(t_a + 16 * c, p);
-        if (c < 3) tmem_wait_ld32(r[(c + 1) & 1]);
-    }
-    tmem_wait_st();
-}
-
 // packed fp32 FMA (Blackwell FFMA2): d = a * b + c on two lanes
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     uint64_t ra, rb, rc, rd;

@@ -321,18 +321,23 @@ __global__ void __launch_bounds__(128) k_composite_chunk(CompArgs a, RayState st
         }
         off += __popc(have);
     }
-    if (!active) return;
     // slots consumed this round: terminated at sample (step+1); ran dry at slot cnt+1 (delta == 0 terminator)
-    const bool dead = terminated || cnt < budget;
+    const bool dead = active && (terminated || cnt < budget);
+    const uint32_t k = a.slots_before + (terminated ? step + 1 : cnt + 1);       // termination slot (1-based)
+    // termination histogram, warp-aggregated: lanes with the same slot elect one lane that adds their count.  (In the May configuration
+    // the 59 % of rays that miss the occupied region all die at slot 1: 155 K same-address atomics made this kernel 4x slower than the
+    // 5x larger benchmark round.)
+    const bool counts = dead && !a.budget_from_ctl && k <= a.max_steps;
+    const uint32_t peers = __match_any_sync(0xffffffffu, counts ? k : 0xffffffffu);
+    if (counts && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(ctl + CTL_HIST + k, (uint32_t)__popc(peers));
+    if (!active) return;
     const uint32_t composited = terminated ? step + 1 : cnt;
     st.nsamp[n] += (int)composited;
     st.wsum[n] = weight_sum; st.depth[n] = d;
     st.img[3 * (size_t)n] = r; st.img[3 * (size_t)n + 1] = g; st.img[3 * (size_t)n + 2] = b;
     if (dead) {
         st.alive[n] = 0;
-        const uint32_t k = a.slots_before + (terminated ? step + 1 : cnt + 1);   // termination slot (1-based)
         st.term[n] = (int)k;
-        if (!a.budget_from_ctl && k <= a.max_steps) atomicAdd(ctl + CTL_HIST + k, 1u);
     } else {
         st.t[n] = t;
     }
@@ -342,7 +347,12 @@ __global__ void __launch_bounds__(128) k_composite_chunk(CompArgs a, RayState st
 // replay of the host loop (renderer.py:326-351)
 // ======================================================================================
 __global__ void k_schedule(uint32_t N, uint32_t max_steps, uint32_t* __restrict__ ctl) {
-    if (threadIdx.x || blockIdx.x) return;
+    // the histogram is staged into shared memory by the whole block first: the replay itself is a serial dependence chain and used to pay
+    // one global-memory round trip per slot (36 us at max_steps = 128)
+    __shared__ uint32_t hist[RENDER_MAX_STEPS + 1];
+    for (uint32_t k = threadIdx.x; k <= max_steps; k += blockDim.x) hist[k] = k ? ctl[CTL_HIST + k] : 0;
+    __syncthreads();
+    if (threadIdx.x) return;
     uint32_t alive = N, step = 0;
     while (step < max_steps) {
         if (alive == 0) break;
@@ -350,7 +360,7 @@ __global__ void k_schedule(uint32_t N, uint32_t max_steps, uint32_t* __restrict_
         n_step = n_step > 8 ? 8 : n_step;
         n_step = n_step < 1 ? 1 : n_step;
         uint32_t died = 0;
-        for (uint32_t k = step + 1; k <= step + n_step && k <= max_steps; k++) died += ctl[CTL_HIST + k];
+        for (uint32_t k = step + 1; k <= step + n_step && k <= max_steps; k++) died += hist[k];
         alive -= died;
         step += n_step;
     }
@@ -1065,7 +1075,7 @@ GF_API int gf_render_frame(const GfModel* model, const GfFrame* f, const GfOut* 
         launches += 2 + field_kernels;
     }
     // schedule replay -> S_total; extra round with device-side budget
-    k_schedule<<<1, 32, 0, st>>>(N, f->max_steps, w.ctl);
+    k_schedule<<<1, 128, 0, st>>>(N, f->max_steps, w.ctl);
     ma.budget = 0; ma.budget_from_ctl = 1;
     k_march_chunk<<<div_up(N, 128), 128, 0, st>>>(ma, w.st, w.sb, w.ctl);
     if ((rc = field())) return rc;

@@ -79,12 +79,56 @@ def run(steps=20, warmup=5, local=0, rays=4096, amp=False):
         torch.cuda.synchronize()
     rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:12]
     tot = sum(r.device_time_total for r in prof.key_averages()) or 1.0
+    graph_ms = graphed_step_ms(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args)
     ref_line = reference_train_step(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args)
     line = {"metric": "train step, %d rays (march_rays_train + field + composite + backward + Adam)" % args.rays, "ms_per_step": ms, "amp": bool(args.amp),
-            "reference_cuda": ref_line, "mean_count": int(model.mean_count), "grid_backward": os.environ.get("GF_GRID_BWD", "b200 (privatised small levels)"),
+            "reference_cuda": ref_line, "mean_count": int(model.mean_count), "cuda_graph": graph_ms, "grid_backward": os.environ.get("GF_GRID_BWD", "b200 (privatised small levels)"),
             "rays_per_s": args.rays / (ms / 1000.0), "loss": float(loss), "grads_finite": bool(all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)),
             "top_kernels": [{"name": r.key[:70], "share": r.device_time_total / tot, "calls": r.count} for r in rows]}
     return line
+
+
+def graphed_step_ms(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args):
+    """The same training step captured ONCE into a CUDA graph (forward through the libgfrender operators, loss, backward, Adam with
+    capturable state) and replayed: with a fixed sample budget (mean_count > 0) the step has no host synchronisation, so the ~300
+    launches the eager step pays for one by one (the 4096-ray step is host-bound in both implementations) collapse into one replay."""
+    import torch
+    try:
+        params = [p for p in model.parameters() if p.requires_grad]
+        opt = torch.optim.Adam(params, lr=1e-3, capturable=True)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast('cuda', dtype=torch.float16, enabled=args.amp):
+                out = model.render(rays_o, rays_d, fi['cond'], bgc, fi['poses6'], index=0, dt_gamma=hp['dt_gamma'], bg_color=bg_color, perturb=True,
+                                   force_all_rays=False, max_steps=hp['max_steps'])
+                loss = ((out['rgb_map'].float() - target) ** 2).mean()
+            loss.backward()
+            opt.step()
+            return loss
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss = step()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        return {"ms_per_step": ms, "rays_per_s": args.rays / (ms / 1000.0), "loss": float(loss), "finite": bool(torch.isfinite(loss))}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:300]}
 
 
 def reference_train_step(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args):
