@@ -20,11 +20,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--amp", action="store_true", help="fp16 autocast + GradScaler on both arms (the reference trains with amp: true)")
+    ap.add_argument("--graph-only", action="store_true", help="(internal) only the CUDA-graph-captured step, in its own process")
     args = ap.parse_args()
-    print(json.dumps(run(args.steps, args.warmup, 0, args.rays, args.amp)), flush=True)
+    print(json.dumps(run(args.steps, args.warmup, 0, args.rays, args.amp, args.graph_only)), flush=True)
 
 
-def run(steps=20, warmup=5, local=0, rays=4096, amp=False):
+def run(steps=20, warmup=5, local=0, rays=4096, amp=False, graph_only=False):
     args = argparse.Namespace(steps=steps, warmup=warmup, rays=rays, amp=amp)
     import torch
     from geneface_b200 import synthetic, utils
@@ -58,6 +59,9 @@ def run(steps=20, warmup=5, local=0, rays=4096, amp=False):
         return loss
 
     step()
+    if graph_only:
+        model.mean_count = int(model.step_counter[(model.local_step - 1) % 16, 0].item() * 1.1)
+        return graphed_step_ms(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args)
     # steady state: the sample budget M comes from the running mean of the previous steps (update_extra_state, renderer.py:255-258), so
     # march_rays_train does not synchronise on the sample count; the mean of this (static) batch + 10 % plays that role here
     model.mean_count = int(model.step_counter[(model.local_step - 1) % 16, 0].item() * 1.1)
@@ -79,8 +83,15 @@ def run(steps=20, warmup=5, local=0, rays=4096, amp=False):
         torch.cuda.synchronize()
     rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:12]
     tot = sum(r.device_time_total for r in prof.key_averages()) or 1.0
-    graph_ms = graphed_step_ms(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args)
     ref_line = reference_train_step(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args)
+    # the graph-captured step runs in its own process: a failed capture must not leave this process's RNG / context in capture mode
+    import subprocess
+    try:
+        cmd = [sys.executable, os.path.abspath(__file__), "--graph-only", "--rays", str(args.rays), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        r = subprocess.run(cmd + (["--amp"] if args.amp else []), capture_output=True, text=True, timeout=240)
+        graph_ms = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else {"unavailable": (r.stderr or r.stdout)[-400:]}
+    except Exception as e:  # noqa: BLE001
+        graph_ms = {"unavailable": repr(e)[:300]}
     line = {"metric": "train step, %d rays (march_rays_train + field + composite + backward + Adam)" % args.rays, "ms_per_step": ms, "amp": bool(args.amp),
             "reference_cuda": ref_line, "mean_count": int(model.mean_count), "cuda_graph": graph_ms, "grid_backward": os.environ.get("GF_GRID_BWD", "b200 (privatised small levels)"),
             "rays_per_s": args.rays / (ms / 1000.0), "loss": float(loss), "grads_finite": bool(all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)),
@@ -128,7 +139,8 @@ def graphed_step_ms(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args):
         ms = e0.elapsed_time(e1) / args.steps
         return {"ms_per_step": ms, "rays_per_s": args.rays / (ms / 1000.0), "loss": float(loss), "finite": bool(torch.isfinite(loss))}
     except Exception as e:  # noqa: BLE001
-        return {"unavailable": repr(e)[:300]}
+        import traceback
+        return {"unavailable": repr(e)[:600], "trace": traceback.format_exc()[-1500:]}
 
 
 def reference_train_step(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args):
