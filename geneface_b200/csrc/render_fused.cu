@@ -587,8 +587,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) k_torso_field(ModelDev m, To
         }
         __syncthreads();
         // deformation MLP 42(+pose,code via bias) -> 64 -> 64 -> 2
-        dense_tile(X, 42, m.w + m.td_wt0, 64, 64, P, bias_deform, true, wstage);
-        dense_tile(P, 64, m.w + m.td_wt1, 64, 64, Q, nullptr, true, wstage);
+        dense_tile_narrow<4>(X, 42, m.w + m.td_wt0, 64, P, bias_deform, true, wstage);
+        dense_tile_narrow<4>(P, 64, m.w + m.td_wt1, 64, Q, nullptr, true, wstage);
         dense_small(Q, 64, m.w + m.td_w2, 2, misc + 2 * 128, misc + 8 * 128);
         if (tid < TILE_S) {
             // x = (x + dx).clamp(-1, 1); grid input (x+1)/2
@@ -609,8 +609,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) k_torso_field(ModelDev m, To
         }
         __syncthreads();
         // canonical MLP (32 + 42 (+pose,code via bias)) -> 32 -> 32 -> 4, sigmoid
-        dense_tile(Fq, 74, m.w + m.tc_wt0, 32, 32, P, bias_canon, true, wstage);
-        dense_tile(P, 32, m.w + m.tc_wt1, 32, 32, Q, nullptr, true, wstage);
+        dense_tile_narrow<2>(Fq, 74, m.w + m.tc_wt0, 32, P, bias_canon, true, wstage);
+        dense_tile_narrow<2>(P, 32, m.w + m.tc_wt1, 32, Q, nullptr, true, wstage);
         dense_small(Q, 32, m.w + m.tc_w2, 4, misc + 4 * 128, misc + 8 * 128);
         if (tid < TILE_S) {
             const uint32_t i = base + tid;
