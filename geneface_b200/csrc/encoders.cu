@@ -199,108 +199,64 @@ __global__ void __launch_bounds__(256) k_grid_forward(const float* __restrict__ 
     }
 }
 
-// K14.  thread = (sample, level, channel pair); vector reductions into grad_grid.
-template <typename T, int D, int C, int N_C>
-__global__ void __launch_bounds__(256) k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
-                                                        const int* __restrict__ offsets, T* __restrict__ grad_grid_all, uint32_t B,
-                                                        uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
-                                                        uint32_t interp) {
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t b = gtid * N_C / C;
-    if (b >= B) return;
-    const uint32_t level = blockIdx.y;
-    const uint32_t ch = gtid * N_C - b * C;
-    T* grad_grid = grad_grid_all + (size_t)(uint32_t)offsets[level] * C;
-    const float* in = inputs + (size_t)b * D;
-    const T* g = grad + (size_t)level * B * C + (size_t)b * C + ch;
-    const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
-    float scale; uint32_t resolution;
-    level_geometry(level, S, H, scale, resolution);
-
-    float pos[D];
-    uint32_t pos_grid[D];
-    #pragma unroll
-    for (int d = 0; d < D; d++) {
-        const float x = in[d];
-        if (x < 0 || x > 1) return;
-        pos[d] = __fmaf_rn(x, scale, align_corners ? 0.0f : 0.5f);
-        pos_grid[d] = (uint32_t)floorf(pos[d]);
-        pos[d] = __fsub_rn(pos[d], (float)pos_grid[d]);
-        if (interp == 1) pos[d] = pos[d] * pos[d] * (3.0f - 2.0f * pos[d]);
-    }
-    float gc[N_C];
-    #pragma unroll
-    for (int c = 0; c < N_C; c++) gc[c] = to_float(g[c]);
-
-    #pragma unroll
-    for (int idx = 0; idx < (1 << D); idx++) {
-        float w = 1;
-        uint32_t pgl[D];
-        #pragma unroll
-        for (int d = 0; d < D; d++) {
-            if ((idx & (1 << d)) == 0) { w *= 1 - pos[d]; pgl[d] = pos_grid[d]; }
-            else { w *= pos[d]; pgl[d] = pos_grid[d] + 1; }
-        }
-        const uint32_t e = grid_index<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
-        T* dst = grad_grid + (size_t)e * C + ch;
-        if constexpr (std::is_same<T, float>::value) {
-            if constexpr (N_C == 2) {
-                // one 8-byte vector reduction (RED.E.ADD.F32x2 on sm_90+) instead of two scalar atomics
-                atomicAdd(reinterpret_cast<float2*>(dst), make_float2(w * gc[0], w * gc[1]));
-            } else {
-                atomicAdd(dst, w * gc[0]);
-            }
-        } else {
-            if constexpr (N_C == 2) {
-                atomicAdd(reinterpret_cast<__half2*>(dst), __floats2half2_rn(w * gc[0], w * gc[1]));
-            } else {
-                atomicAdd(reinterpret_cast<__half*>(dst), __float2half_rn(w * gc[0]));
-            }
-        }
-    }
-}
-
-// K14, B200 form (fp32 or fp16 gradients, C == 2, D == 2 or 3): level-major grid (blockIdx.y = level), one thread per sample carrying both
-// channels, grid-stride over the samples.
+// K14, B200 form: level-major grid (blockIdx.y = level), one thread per sample carrying all C channels, grid-stride over the samples.
 //   * SMALL DENSE LEVELS (table <= the CTA's shared-memory budget: 3-D levels 0-1 = 4,920 / 13,824 entries, 2-D levels 0-6 of the May
-//     configuration) are where the reference's global atomics collide hardest: every sample of the batch lands in a few thousand entries
-//     (level 0: ~800 updates per entry per step at 0.5 M samples).  Here `priv_ctas` CTAs per such level each accumulate their share of the
-//     samples into a PRIVATE shared-memory copy of the level (shared-memory reductions, no L2 round trip, no cross-SM contention) and flush
-//     only the touched entries with one 8-byte vector reduction each: <= priv_ctas * entries global reductions instead of 2^D * B.
-//   * the other levels keep one 8-byte vector reduction per corner (RED.E.ADD.F32x2 / .F16x2): their updates are spread over >= 32 K entries
-//     and are bound by L2 reduction throughput, not by contention.
-// The sum order differs from the reference's (which is itself non-deterministic: atomics); parity is checked against an fp64 re-accumulation.
-// One (entry, gradient pair) update.  When EVERY lane of a full warp targets the same entry -- samples of one ray inside one coarse cell, or
-// ambient coordinates clustered in a few cells of the 2-D grid: the dominant pattern behind the measured contention -- the warp tree-reduces
-// the 32 contributions with shuffles and commits once instead of serialising 32 same-address reductions.
-template <typename Commit>
-__device__ __forceinline__ void grid_update(uint32_t e, float a, float b, Commit&& commit) {
-    const uint32_t active = __activemask();
-    if (active == 0xffffffffu && __match_any_sync(0xffffffffu, e) == 0xffffffffu) {
+//     configuration) are where global atomics collide hardest: every sample of the batch lands in a few thousand entries (level 0: ~800
+//     updates per entry per step at 0.5 M samples).  `priv_ctas` CTAs per such level each accumulate their share of the samples into a
+//     PRIVATE shared-memory copy of the level (shared-memory reductions, no L2 round trip, no cross-SM contention) and flush only the
+//     touched entries with vector reductions: <= priv_ctas * entries global reductions instead of 2^D * B.
+//   * when EVERY lane of a warp targets the same entry -- samples of one ray inside one coarse cell, or ambient coordinates clustered in a
+//     few cells of the 2-D grid: the dominant pattern behind the measured contention -- the warp tree-reduces the 32 contributions with
+//     shuffles and commits once instead of serialising 32 same-address reductions;
+//   * everything else is one 8-byte vector reduction per channel pair (RED.E.ADD.F32x2 / .F16x2) per corner.
+// The sum order differs from the reference's (which is itself non-deterministic: atomics); parity is checked against an fp64
+// re-accumulation.  Measured (profiles/r02_summary.md): 65,536-ray step 25.1 ms (plain reductions) -> 17.9 (privatised) -> 16.0 (+ warp
+// aggregation); at 4,096 rays privatisation loses, so it is switched on from 131,072 samples.
+template <int C, typename Commit>
+__device__ __forceinline__ void grid_update(uint32_t e, float (&v)[C], Commit&& commit) {
+    if (__activemask() == 0xffffffffu && __match_any_sync(0xffffffffu, e) == 0xffffffffu) {
         #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-        if ((threadIdx.x & 31) == 0) commit(e, a, b);
+        for (int c = 0; c < C; c++) {
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+        }
+        if ((threadIdx.x & 31) == 0) commit(e, v);
     } else {
-        commit(e, a, b);
+        commit(e, v);
     }
 }
 
-template <typename T, int D>
+template <typename T, int C>
+__device__ __forceinline__ void grid_reduce_global(T* __restrict__ grad_grid, uint32_t e, const float (&v)[C]) {
+    T* dst = grad_grid + (size_t)e * C;
+    if constexpr (C == 1) {
+        if constexpr (std::is_same<T, float>::value) atomicAdd(dst, v[0]);
+        else atomicAdd(reinterpret_cast<__half*>(dst), __float2half_rn(v[0]));
+    } else {
+        #pragma unroll
+        for (int c = 0; c < C; c += 2) {
+            if constexpr (std::is_same<T, float>::value) atomicAdd(reinterpret_cast<float2*>(dst + c), make_float2(v[c], v[c + 1]));
+            else atomicAdd(reinterpret_cast<__half2*>(dst + c), __floats2half2_rn(v[c], v[c + 1]));
+        }
+    }
+}
+
+template <typename T, int D, int C>
 __global__ void __launch_bounds__(256) k_grid_backward_b200(const T* __restrict__ grad, const float* __restrict__ inputs,
                                                              const int* __restrict__ offsets, T* __restrict__ grad_grid_all, uint32_t B,
                                                              uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
                                                              uint32_t interp, uint32_t priv_ctas, uint32_t priv_entries) {
-    extern __shared__ float2 tab[];
+    extern __shared__ float tab[];                        // private copy of a small level: [hashmap_size][C] fp32
     const uint32_t level = blockIdx.y;
     const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
     const bool priv = hashmap_size <= priv_entries;
     if (priv && blockIdx.x >= priv_ctas) return;
     const uint32_t nctas = priv ? (priv_ctas < gridDim.x ? priv_ctas : gridDim.x) : gridDim.x;
-    T* grad_grid = grad_grid_all + (size_t)(uint32_t)offsets[level] * 2;
+    T* grad_grid = grad_grid_all + (size_t)(uint32_t)offsets[level] * C;
     float scale; uint32_t resolution;
     level_geometry(level, S, H, scale, resolution);
     if (priv) {
-        for (uint32_t e = threadIdx.x; e < hashmap_size; e += blockDim.x) tab[e] = make_float2(0.f, 0.f);
+        for (uint32_t e = threadIdx.x; e < hashmap_size * C; e += blockDim.x) tab[e] = 0.f;
         __syncthreads();
     }
     for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += nctas * blockDim.x) {
@@ -318,8 +274,10 @@ __global__ void __launch_bounds__(256) k_grid_backward_b200(const T* __restrict_
             if (interp == 1) pos[d] = pos[d] * pos[d] * (3.0f - 2.0f * pos[d]);
         }
         if (oob) continue;                                  // gridencoder.cu:281-286: out-of-range inputs get no gradient
-        const T* g = grad + (size_t)level * B * 2 + (size_t)b * 2;
-        const float g0 = to_float(g[0]), g1 = to_float(g[1]);
+        const T* g = grad + (size_t)level * B * C + (size_t)b * C;
+        float gc[C];
+        #pragma unroll
+        for (int c = 0; c < C; c++) gc[c] = to_float(g[c]);
         #pragma unroll
         for (int idx = 0; idx < (1 << D); idx++) {
             float w = 1;
@@ -330,33 +288,37 @@ __global__ void __launch_bounds__(256) k_grid_backward_b200(const T* __restrict_
                 else { w *= pos[d]; pgl[d] = pos_grid[d] + 1; }
             }
             const uint32_t e = grid_index<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
+            float v[C];
+            #pragma unroll
+            for (int c = 0; c < C; c++) v[c] = w * gc[c];
             if (priv) {
-                grid_update(e, w * g0, w * g1, [&](uint32_t ee, float a, float b) { atomicAdd(&tab[ee].x, a); atomicAdd(&tab[ee].y, b); });
-            } else if constexpr (std::is_same<T, float>::value) {
-                grid_update(e, w * g0, w * g1, [&](uint32_t ee, float a, float b) { atomicAdd(reinterpret_cast<float2*>(grad_grid + (size_t)ee * 2), make_float2(a, b)); });
+                grid_update<C>(e, v, [&](uint32_t ee, const float (&vv)[C]) {
+                    #pragma unroll
+                    for (int c = 0; c < C; c++) atomicAdd(&tab[(size_t)ee * C + c], vv[c]);
+                });
             } else {
-                grid_update(e, w * g0, w * g1, [&](uint32_t ee, float a, float b) { atomicAdd(reinterpret_cast<__half2*>(grad_grid + (size_t)ee * 2), __floats2half2_rn(a, b)); });
+                grid_update<C>(e, v, [&](uint32_t ee, const float (&vv)[C]) { grid_reduce_global<T, C>(grad_grid, ee, vv); });
             }
         }
     }
     if (priv) {
         __syncthreads();
         for (uint32_t e = threadIdx.x; e < hashmap_size; e += blockDim.x) {
-            const float2 v = tab[e];
-            if (v.x != 0.f || v.y != 0.f) {
-                if constexpr (std::is_same<T, float>::value) atomicAdd(reinterpret_cast<float2*>(grad_grid + (size_t)e * 2), v);
-                else atomicAdd(reinterpret_cast<__half2*>(grad_grid + (size_t)e * 2), __floats2half2_rn(v.x, v.y));
-            }
+            float v[C];
+            bool any = false;
+            #pragma unroll
+            for (int c = 0; c < C; c++) { v[c] = tab[(size_t)e * C + c]; any = any || v[c] != 0.f; }
+            if (any) grid_reduce_global<T, C>(grad_grid, e, v);
         }
     }
 }
 
-constexpr uint32_t GRID_BWD_PRIV_ENTRIES = 13824;            // 3-D level 1 of the May configuration: 110,592 B of shared memory, 2 CTAs / SM
+constexpr uint32_t GRID_BWD_PRIV_BYTES = 13824 * 8;           // 3-D level 1 of the May configuration (C = 2): 110,592 B, 2 CTAs / SM
 
-// GF_GRID_BWD=legacy selects the reference-shaped kernel (one thread per sample x level x channel pair, every corner a global reduction): A/B runs
-static bool grid_bwd_legacy() {
-    static const int v = [] { const char* e = getenv("GF_GRID_BWD"); return (e && !strcmp(e, "legacy")) ? 1 : 0; }();
-    return v == 1;
+// GF_GRID_BWD=plain forces plain vector reductions (no privatisation), GF_GRID_BWD=priv forces privatisation at any batch size: A/B runs
+static int grid_bwd_mode() {
+    static const int v = [] { const char* e = getenv("GF_GRID_BWD"); return !e ? 0 : (!strcmp(e, "plain") || !strcmp(e, "legacy")) ? 1 : !strcmp(e, "priv") ? 2 : 0; }();
+    return v;
 }
 
 // K15  gridencoder.cu:342-368
@@ -441,38 +403,23 @@ template <typename T, int D, int C>
 static int launch_grid_backward(const void* grad, const float* inputs, const int* offsets, void* grad_emb, uint32_t B, uint32_t L, float S,
                                 uint32_t H, const void* dy_dx, void* grad_inputs, uint32_t gridtype, bool ac, uint32_t interp,
                                 cudaStream_t st) {
-    constexpr int N_C = C < 2 ? C : 2;
-    int rc;
-    if constexpr (C == 2 && (D == 2 || D == 3)) {
-        if (!grid_bwd_legacy()) {
-            static bool attr = false;
-            if (!attr) {
-                cudaFuncSetAttribute(k_grid_backward_b200<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GRID_BWD_PRIV_ENTRIES * sizeof(float2)));
-                attr = true;
-            }
-            // Privatisation pays only when the batch is large enough that (a) contention on the small levels is real and (b) every
-            // privatising CTA still sees thousands of samples (zero + flush cost one pass over the level's table each).  Measured on
-            // B200 (profiles/r02_summary.md): at 27.5 K samples (4096 rays, BASELINE.json configs[4]) the plain vector reductions are
-            // 3x faster than 3 privatising CTAs per level, so small batches keep them (priv_entries = 0).
-            const bool use_priv = B >= 131072 || (getenv("GF_GRID_BWD") && !strcmp(getenv("GF_GRID_BWD"), "priv"));
-            uint32_t priv_ctas = B / 4096;
-            priv_ctas = priv_ctas < 8 ? 8 : (priv_ctas > 64 ? 64 : priv_ctas);
-            uint32_t gx = div_up(B, 256 * 4);
-            gx = gx < priv_ctas ? priv_ctas : (gx > 1024 ? 1024 : gx);
-            k_grid_backward_b200<T, D><<<dim3(gx, L, 1), 256, GRID_BWD_PRIV_ENTRIES * sizeof(float2), st>>>(
-                (const T*)grad, inputs, offsets, (T*)grad_emb, B, L, S, H, gridtype, ac, interp, priv_ctas, use_priv ? GRID_BWD_PRIV_ENTRIES : 0u);
-            rc = check_launch("grid_encode_backward(b200)");
-            if (rc) return rc;
-            if (dy_dx && grad_inputs) {
-                k_grid_input_backward<T, D, C><<<div_up(B * D, 256), 256, 0, st>>>((const T*)grad, (const T*)dy_dx, (T*)grad_inputs, B, L);
-                rc = check_launch("grid_encode_backward(inputs)");
-            }
-            return rc;
-        }
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_grid_backward_b200<T, D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRID_BWD_PRIV_BYTES);
+        attr = true;
     }
-    const dim3 grid(div_up(B * C / N_C, 256), L, 1);
-    k_grid_backward<T, D, C, N_C><<<grid, 256, 0, st>>>((const T*)grad, inputs, offsets, (T*)grad_emb, B, L, S, H, gridtype, ac, interp);
-    rc = check_launch("grid_encode_backward");
+    // Privatisation pays only when the batch is large enough that (a) contention on the small levels is real and (b) every privatising
+    // CTA still sees thousands of samples (zero + flush cost one pass over the level's table each).
+    const int mode = grid_bwd_mode();
+    const bool use_priv = mode == 2 || (mode == 0 && B >= 131072);
+    uint32_t priv_ctas = B / 4096;
+    priv_ctas = priv_ctas < 8 ? 8 : (priv_ctas > 64 ? 64 : priv_ctas);
+    uint32_t gx = div_up(B, 256 * 4);
+    gx = gx < priv_ctas ? priv_ctas : (gx > 1024 ? 1024 : gx);
+    k_grid_backward_b200<T, D, C><<<dim3(gx, L, 1), 256, GRID_BWD_PRIV_BYTES, st>>>(
+        (const T*)grad, inputs, offsets, (T*)grad_emb, B, L, S, H, gridtype, ac, interp, priv_ctas,
+        use_priv ? GRID_BWD_PRIV_BYTES / (uint32_t)(C * sizeof(float)) : 0u);
+    int rc = check_launch("grid_encode_backward");
     if (rc) return rc;
     if (dy_dx && grad_inputs) {
         k_grid_input_backward<T, D, C><<<div_up(B * D, 256), 256, 0, st>>>((const T*)grad, (const T*)dy_dx, (T*)grad_inputs, B, L);

@@ -266,11 +266,11 @@ def test_grid_encoder(oracle_ops, D, gridtype, interp):
     assert_close((0.5 * out + o_b).cpu().numpy(), o_c.cpu().numpy(), rel=1e-4, abs_=1e-5, what="linearity")
 
 
-@pytest.mark.parametrize("mode", ["priv", "legacy"])
+@pytest.mark.parametrize("mode", ["priv", "plain"])
 @pytest.mark.parametrize("D", [2, 3])
 def test_grid_backward_kernels_and_fp16_path(oracle_ops, D, mode):
     """Hash-grid backward in both kernel forms -- `priv`: shared-memory privatised small levels + vector
-    reductions (forced here; by default chosen for batches >= 131,072 samples), `legacy`: one vector reduction per corner -- against the
+    reductions (forced here; by default chosen for batches >= 131,072 samples), `plain`: one vector reduction per corner (+ the warp-uniform aggregation) -- against the
     oracle's fp64 re-accumulation of the same scatter, on a LARGE batch (the regime privatisation is for), in fp32 and through the
     fp16 path (dtype = 1: half gradients, half2 reductions, as the reference runs under autocast, grid.py:43-44,65-89).
     The mode is latched at first use per process, so each runs in a child process."""
