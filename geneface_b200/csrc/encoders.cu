@@ -58,11 +58,6 @@ __device__ __forceinline__ void level_geometry(uint32_t level, float S, uint32_t
     resolution = (uint32_t)ceilf(scale) + 1;
 }
 
-template <typename T, int C>
-struct Feat {
-    float v[C];
-};
-
 // one vector load of the C channels of table entry `e`
 template <typename T, int C>
 __device__ __forceinline__ void load_entry(const T* __restrict__ grid, uint32_t e, float (&out)[C]) {
@@ -92,6 +87,12 @@ __device__ __forceinline__ float to_float(float x) { return x; }
 __device__ __forceinline__ float to_float(__half x) { return __half2float(x); }
 
 // K13.  grid = (ceil(B/256), L); thread = one (sample, level).
+// The 2^D corner entries are gathered ONCE into registers (one vector load each) and serve both the interpolated output and, when asked
+// for, the input Jacobian dy_dx: the derivative along dimension g is the same multilinear sum over the other dimensions applied to the
+// corner DIFFERENCES corner[idx | bit g] - corner[idx].  (The reference gathers the corners a second time for dy_dx, 2^(D-1) * 2 * D more
+// loads per sample and level, gridencoder.cu:200-243.)  The fp32 operation order of both results is the reference's -- corner order
+// idx = 0 .. 2^D - 1 with FFMA accumulation for the output; scale * prod(w_d) * diff * deriv summed over the sub-corners in ascending
+// order for the Jacobian -- so the outputs stay bit-identical to it.
 template <typename T, int D, int C>
 __global__ void __launch_bounds__(256) k_grid_forward(const float* __restrict__ inputs, const T* __restrict__ grid_all,
                                                        const int* __restrict__ offsets, T* __restrict__ outputs, uint32_t B, uint32_t L,
@@ -100,102 +101,84 @@ __global__ void __launch_bounds__(256) k_grid_forward(const float* __restrict__ 
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const uint32_t level = blockIdx.y;
-    const T* grid = grid_all + (size_t)(uint32_t)offsets[level] * C;
-    const float* in = inputs + (size_t)b * D;
-    T* out = outputs + (size_t)level * B * C + (size_t)b * C;
-    T* dd = dy_dx ? dy_dx + (size_t)b * D * L * C + (size_t)level * D * C : nullptr;
+    T* out = outputs + ((size_t)level * B + b) * C;
+    T* jac = dy_dx ? dy_dx + ((size_t)b * L + level) * D * C : nullptr;
 
-    float x[D];
-    bool oob = false;
+    float frac[D], dfrac[D];           // interpolation weight of the upper corner per dimension, and its derivative w.r.t. the cell coordinate
+    uint32_t cell[D];
+    bool inside = true;
+    float scale; uint32_t resolution;
+    level_geometry(level, S, H, scale, resolution);
     #pragma unroll
     for (int d = 0; d < D; d++) {
-        x[d] = in[d];
-        if (x[d] < 0 || x[d] > 1) oob = true;
+        const float x = inputs[(size_t)b * D + d];
+        inside = inside && x >= 0 && x <= 1;
+        float p = __fmaf_rn(x, scale, align_corners ? 0.0f : 0.5f);
+        cell[d] = (uint32_t)floorf(p);
+        p = __fsub_rn(p, (float)cell[d]);
+        if (interp == 1) { dfrac[d] = 6 * p * (1.0f - p); p = p * p * (3.0f - 2.0f * p); }     // smoothstep
+        else dfrac[d] = 1.0f;
+        frac[d] = p;
     }
-    if (oob) {
+    if (!inside) {                     // gridencoder.cu:110-135: samples outside [0,1]^D encode to zero
         #pragma unroll
         for (int c = 0; c < C; c++) out[c] = from_float<T>(0.f);
-        if (dd) {
+        if (jac) {
             #pragma unroll
-            for (int i = 0; i < D * C; i++) dd[i] = from_float<T>(0.f);
+            for (int i = 0; i < D * C; i++) jac[i] = from_float<T>(0.f);
         }
         return;
     }
-    const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
-    float scale; uint32_t resolution;
-    level_geometry(level, S, H, scale, resolution);
+    const T* table = grid_all + (size_t)(uint32_t)offsets[level] * C;
+    const uint32_t entries = (uint32_t)(offsets[level + 1] - offsets[level]);
 
-    float pos[D], pos_deriv[D];
-    uint32_t pos_grid[D];
+    float corner[1 << D][C];
     #pragma unroll
-    for (int d = 0; d < D; d++) {
-        pos[d] = __fmaf_rn(x[d], scale, align_corners ? 0.0f : 0.5f);
-        pos_grid[d] = (uint32_t)floorf(pos[d]);
-        pos[d] = __fsub_rn(pos[d], (float)pos_grid[d]);
-        if (interp == 1) {
-            pos_deriv[d] = 6 * pos[d] * (1.0f - pos[d]);
-            pos[d] = pos[d] * pos[d] * (3.0f - 2.0f * pos[d]);
-        } else pos_deriv[d] = 1.0f;
+    for (int idx = 0; idx < (1 << D); idx++) {
+        uint32_t pg[D];
+        #pragma unroll
+        for (int d = 0; d < D; d++) pg[d] = cell[d] + ((idx >> d) & 1);
+        load_entry<T, C>(table, grid_index<D>(gridtype, align_corners, entries, resolution, pg), corner[idx]);
     }
-
-    T results[C];
+    T acc[C];
     #pragma unroll
-    for (int c = 0; c < C; c++) results[c] = from_float<T>(0.f);
+    for (int c = 0; c < C; c++) acc[c] = from_float<T>(0.f);
     #pragma unroll
     for (int idx = 0; idx < (1 << D); idx++) {
         float w = 1;
-        uint32_t pgl[D];
         #pragma unroll
-        for (int d = 0; d < D; d++) {
-            if ((idx & (1 << d)) == 0) { w = __fmul_rn(w, __fsub_rn(1.0f, pos[d])); pgl[d] = pos_grid[d]; }
-            else { w = __fmul_rn(w, pos[d]); pgl[d] = pos_grid[d] + 1; }
-        }
-        const uint32_t e = grid_index<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
-        float g[C];
-        load_entry<T, C>(grid, e, g);
+        for (int d = 0; d < D; d++) w = __fmul_rn(w, ((idx >> d) & 1) ? frac[d] : __fsub_rn(1.0f, frac[d]));
         #pragma unroll
-        for (int c = 0; c < C; c++) results[c] = from_float<T>(__fmaf_rn(w, g[c], to_float(results[c])));
+        for (int c = 0; c < C; c++) acc[c] = from_float<T>(__fmaf_rn(w, corner[idx][c], to_float(acc[c])));
     }
     if constexpr (std::is_same<T, float>::value && C == 2) {
-        *reinterpret_cast<float2*>(out) = make_float2(results[0], results[1]);
+        *reinterpret_cast<float2*>(out) = make_float2(acc[0], acc[1]);
     } else {
         #pragma unroll
-        for (int c = 0; c < C; c++) out[c] = results[c];
+        for (int c = 0; c < C; c++) out[c] = acc[c];
     }
-
-    if (dd) {
-        // gridencoder.cu:200-243
+    if (!jac) return;
+    #pragma unroll
+    for (int g = 0; g < D; g++) {
+        T dg[C];
         #pragma unroll
-        for (int gd = 0; gd < D; gd++) {
-            T rg[C];
+        for (int c = 0; c < C; c++) dg[c] = from_float<T>(0.f);
+        #pragma unroll
+        for (int idx = 0; idx < (1 << D); idx++) {
+            if (idx & (1 << g)) continue;                                   // lower corner along g; its partner is idx | (1 << g)
+            float w = scale;
             #pragma unroll
-            for (int c = 0; c < C; c++) rg[c] = from_float<T>(0.f);
+            for (int d = 0; d < D; d++)
+                if (d != g) w *= ((idx >> d) & 1) ? frac[d] : 1 - frac[d];
             #pragma unroll
-            for (int idx = 0; idx < (1 << (D - 1)); idx++) {
-                float w = scale;
-                uint32_t pgl[D];
-                #pragma unroll
-                for (int nd = 0; nd < D - 1; nd++) {
-                    const int d = (nd >= gd) ? (nd + 1) : nd;
-                    if ((idx & (1 << nd)) == 0) { w *= 1 - pos[d]; pgl[d] = pos_grid[d]; }
-                    else { w *= pos[d]; pgl[d] = pos_grid[d] + 1; }
-                }
-                pgl[gd] = pos_grid[gd];
-                const uint32_t el = grid_index<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
-                pgl[gd] = pos_grid[gd] + 1;
-                const uint32_t er = grid_index<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
-                float gl[C], gr[C];
-                load_entry<T, C>(grid, el, gl);
-                load_entry<T, C>(grid, er, gr);
-                #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    if constexpr (std::is_same<T, float>::value) rg[c] += w * (gr[c] - gl[c]) * pos_deriv[gd];
-                    else rg[c] = from_float<T>(to_float(rg[c]) + w * to_float(from_float<T>(gr[c] - gl[c])) * pos_deriv[gd]);
-                }
+            for (int c = 0; c < C; c++) {
+                const float diff = corner[idx | (1 << g)][c] - corner[idx][c];
+                if constexpr (std::is_same<T, float>::value) dg[c] += w * diff * dfrac[g];
+                else dg[c] = from_float<T>(to_float(dg[c]) + w * to_float(from_float<T>(diff)) * dfrac[g]);
             }
-            #pragma unroll
-            for (int c = 0; c < C; c++) dd[gd * C + c] = rg[c];
         }
+        #pragma unroll
+        for (int c = 0; c < C; c++) jac[g * C + c] = dg[c];
     }
 }
 
