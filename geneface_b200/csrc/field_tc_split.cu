@@ -27,7 +27,16 @@
 
 namespace gf {
 
-constexpr int SP_THREADS = 512;        // warps 0-7 producers, 8-11 consumer stream 0, 12-15 consumer stream 1
+constexpr int SP_THREADS = 512;        // kernel B: warps 0-7 producers, 8-11 consumer stream 0, 12-15 consumer stream 1
+// kernel A: GF_A_PROD_WG producer warpgroups, default 2 (same warp roles as kernel B).  3 (warps 0-11 producers, 12-15 stream 0, 16-19 stream 1, 96
+// registers per thread) was measured SLOWER: 10.09 vs 8.75 ms per frame.  With a third gathering warpgroup every producer and both consumer streams slow
+// down in proportion (the same 4-level batch takes 3,300 instead of 2,450 cycles, the split epilogue 2,700 instead of 2,050): the SM's issue slots, not
+// the number of gathering warps, bound this kernel (profiles/r02_summary.md section 7).
+#ifndef GF_A_PROD_WG
+#define GF_A_PROD_WG 2
+#endif
+constexpr int SPA_PROD_WG = GF_A_PROD_WG, SPA_PROD_THREADS = 128 * SPA_PROD_WG, SPA_THREADS = SPA_PROD_THREADS + 256;
+static_assert(SPA_PROD_WG == 2 || SPA_PROD_WG == 3, "2 or 3 producer warpgroups");
 constexpr int SP_NSLOT = 6;            // feature-tile ring depth
 constexpr uint32_t SP_TILE_BYTES = 128 * 128;
 
@@ -58,7 +67,12 @@ struct SpSmem {
     static constexpr uint32_t F = W;
     static constexpr uint32_t DIR = F + SP_NSLOT * SP_TILE_BYTES;    // per slot: 128 x float4 view directions (kernel B)
     static constexpr uint32_t BIAS = DIR + SP_NSLOT * 128 * 16;      // 128 floats
-    static constexpr uint32_t BAR = BIAS + 512;                      // wbar, full[NSLOT], empty[NSLOT], mma[2]
+    // per-kernel extras (9 KB): kernel A: W2 = ambient output layer, 64 x float4 {w0[c], w0[c+1], w1[c], w1[c+1]}; POS = 2 x 256 x float4 per-thread
+    // staged sample positions.  kernel B: AP = 2 x 256 x float2 per-thread staged ambient coordinates (over POS), RAY = 3 x 128 x u32 staged ray ids (over W2..)
+    static constexpr uint32_t W2 = BIAS + 512;
+    static constexpr uint32_t POS = W2 + 1024;
+    static constexpr uint32_t AP = POS, RAY = POS + 2 * 256 * 8;
+    static constexpr uint32_t BAR = POS + 2 * 384 * 16;              // wbar, full[NSLOT], empty[NSLOT], mma[2]
     static constexpr uint32_t TMEM = BAR + 8 * (1 + 2 * SP_NSLOT + 2);
     static constexpr uint32_t TOTAL = TMEM + 16;
     static constexpr uint32_t BYTES = TOTAL + 1024;
@@ -114,6 +128,24 @@ __device__ __forceinline__ void stream_wait_mma(uint32_t bar_mma, uint32_t& phas
 }
 
 
+// -DGF_TC_TIMING=1 (experiment builds only): CTA 0 stamps clock64() at every phase boundary of its tiles TT_J0 .. TT_J0+TT_NJ-1 into the
+// gf_tc_debug buffer, read back by scripts/tc_timeline.py.  Layout: long long [kernel 2][who 4: stream 0, stream 1, producer half 0, half 1][TT_NJ][8].
+#ifndef GF_TC_TIMING
+#define GF_TC_TIMING 0
+#endif
+#if GF_TC_TIMING
+constexpr uint32_t TT_J0 = 96, TT_NJ = 64;
+#define TT_STAMP(kern, who, j, k)                                                                                            \
+    do {                                                                                                                     \
+        if (a.dbg && blockIdx.x == 0 && (j) >= TT_J0 && (j) < TT_J0 + TT_NJ)                                                    \
+            reinterpret_cast<long long*>(a.dbg)[((((kern) * 4 + (who)) * TT_NJ) + ((j) - TT_J0)) * 8 + (k)] = clock64();     \
+    } while (0)
+#define TT_LSTAMP(kern, who, j, k) do { if (lead_warp && elect_one_sync()) TT_STAMP(kern, who, j, k); } while (0)
+#else
+#define TT_STAMP(kern, who, j, k) do { } while (0)
+#define TT_LSTAMP(kern, who, j, k) do { } while (0)
+#endif
+
 struct SpArgs {
     GridDesc grid;              // A: 3-D position grid; B: 2-D ambient grid
     float bound, inv2b;
@@ -126,14 +158,14 @@ struct SpArgs {
 
 // common prologue: barriers, TMEM, weights, bias.  Returns the TMEM base.
 template <uint32_t W>
-__device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, const SpArgs& a, const uint32_t* cuts, int ncuts) {
+__device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, const SpArgs& a, const uint32_t* cuts, int ncuts, uint32_t nprod) {
     using L = SpSmem<W>;
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     float* bias = reinterpret_cast<float*>(smem + L::BIAS);
     if (tid == 0) {
         mbar_init(sbase + L::BAR, 1);
         for (int s = 0; s < SP_NSLOT; s++) {
-            mbar_init(sbase + L::BAR + 8 * (1 + s), 256);               // full: every producer thread arrives
+            mbar_init(sbase + L::BAR + 8 * (1 + s), nprod);             // full: every producer thread arrives
             mbar_init(sbase + L::BAR + 8 * (1 + SP_NSLOT + s), 1);      // empty: the stream leader arrives
         }
         mbar_init(sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT), 1);
@@ -258,7 +290,7 @@ __device__ __forceinline__ void gather2_dyn8(const GridDesc& g, int l0, float x,
 }
 
 template <bool DBG>
-__global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
+__global__ void __launch_bounds__(SPA_THREADS, 1) k_tc_amb(const SpArgs a) {
     using L = SpSmem<WA_TOTAL>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -267,15 +299,17 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
     const uint32_t M = a.io.M_dev ? *a.io.M_dev : a.io.M_host;
     if (M == 0) return;                      // e.g. the extra round of a frame whose budget is 0: skip weight staging / TMEM allocation
     const uint32_t cuts[4] = {0, WA_A1H, WA_A1L, WA_TOTAL};
-    const uint32_t tmem_base = sp_setup<WA_TOTAL>(smem, sbase, a, cuts, 3);
-    const float* bias_cond = reinterpret_cast<const float*>(smem + L::BIAS);
+    if (tid < 64)          // ambient output layer -> shared memory (read as broadcast LDS.128 by the consumers); visible after sp_setup's __syncthreads
+        sts128f(sbase + L::W2 + 16 * tid, make_float4(a.w_amb2[2 * tid], a.w_amb2[2 * tid + 1], a.w_amb2[128 + 2 * tid], a.w_amb2[128 + 2 * tid + 1]));
+    const uint32_t tmem_base = sp_setup<WA_TOTAL>(smem, sbase, a, cuts, 3, SPA_PROD_THREADS);
+    const uint32_t bias_cond = sbase + L::BIAS;
     const uint32_t bar_full = sbase + L::BAR + 8, bar_empty = sbase + L::BAR + 8 * (1 + SP_NSLOT);
     const uint32_t num_tiles = (M + 127) / 128;
     const uint32_t my_tiles = num_tiles > blockIdx.x ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (warp < 8) {
+    if (warp < 4 * SPA_PROD_WG) {
         // ------------------------------------------------ producers ------------------------------------------------
-        const uint32_t half = tid >> 7, row = tid & 127;
+        const uint32_t half = tid >> 7, row = tid & 127;     // half = producer warpgroup 0 .. SPA_PROD_WG-1
         uint32_t flat_units = 0;          // bit u: levels 4u..4u+3 all drop z and are not hashed
         #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -284,58 +318,94 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             for (int q = 0; q < 4; q++) flat = flat && a.grid.lv.sz[4 * u + q] == 0 && a.grid.lv.hashed[4 * u + q] == 0;
             flat_units |= (flat ? 1u : 0u) << u;
         }
-        // the row's position is fetched ONE TILE AHEAD (as kernel B does with its inputs): ~10 % of this kernel's warp-stall samples sat on
-        // the position load at the top of the tile (profiles/r02_summary.md)
-        auto fetch_pos = [&](uint32_t j) {
-            float3 p = make_float3(0.f, 0.f, 0.f);
+        // This warpgroup's units (4 levels each) of a row.  Two warpgroups: u = wg and wg + 2 (one 8-corner coarse unit + one z-dropped fine unit
+        // each).  Three: the cheapest pair of units (cost 2 per 8-corner unit, 1 per z-dropped one) shares a warpgroup, the other two units get one each.
+        uint32_t my_u0, my_u1, my_nu;
+        if (SPA_PROD_WG == 2) { my_u0 = half; my_u1 = half + 2; my_nu = 2; }
+        else {
+            uint32_t best = 99, bp = 2, bq = 3;
+            #pragma unroll
+            for (uint32_t p = 0; p < 4; p++)
+                #pragma unroll
+                for (uint32_t q = p + 1; q < 4; q++) {
+                    const uint32_t c = 4 - ((flat_units >> p) & 1) - ((flat_units >> q) & 1);
+                    if (c <= best) { best = c; bp = p; bq = q; }      // <=: prefer the finest pair on ties
+                }
+            uint32_t singles[2], ns = 0;
+            #pragma unroll
+            for (uint32_t u = 0; u < 4; u++) if (u != bp && u != bq) { if (ns == 0) singles[0] = u; else singles[1] = u; ns++; }
+            if (half == 2) { my_u0 = bp; my_u1 = bq; my_nu = 2; }
+            else { my_u0 = half == 0 ? singles[0] : singles[1]; my_u1 = my_u0; my_nu = 1; }
+        }
+        // The row's position is staged ONE TILE AHEAD into this thread's own 16 bytes of shared memory with cp.async (double-buffered).  A plain
+        // register prefetch did not help (8.46 vs 8.48 ms): ptxas put the prefetch LDG on the same scoreboard as the uniform constant loads at the
+        // top of the loop, so the first use of the CURRENT position waited for the NEXT tile's DRAM access (7 % of the kernel's stall samples on
+        // that one FADD, ~750 of the producers' 5,280 cycles per tile; profiles/r02_summary.md section 7).  cp.async completion is tracked by the
+        // async-group counter instead.
+        const uint32_t pos_s = sbase + L::POS + 16 * tid;
+        auto stage_pos = [&](uint32_t j) {
             const uint32_t i = (blockIdx.x + j * gridDim.x) * 128 + row;
             if (j < my_tiles && i < M) {
-                if (a.io.pos4) { const float4 q = a.io.pos4[i]; p = make_float3(q.x, q.y, q.z); }
-                else p = make_float3(a.io.xyzs[3 * (size_t)i], a.io.xyzs[3 * (size_t)i + 1], a.io.xyzs[3 * (size_t)i + 2]);
+                const uint32_t dst = pos_s + (j & 1) * (SPA_PROD_THREADS * 16);
+                if (a.io.pos4) cp_async16(dst, a.io.pos4 + i);
+                else { cp_async4(dst, a.io.xyzs + 3 * (size_t)i); cp_async4(dst + 4, a.io.xyzs + 3 * (size_t)i + 1); cp_async4(dst + 8, a.io.xyzs + 3 * (size_t)i + 2); }
             }
-            return p;
+            cp_async_commit();
         };
-        float3 nxt = fetch_pos(0);
+        stage_pos(0);
         #pragma unroll 1
         for (uint32_t j = 0; j < my_tiles; j++) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
             const uint32_t i = tile * 128 + row;
             const bool valid = i < M;
-            const float x = nxt.x, y = nxt.y, z = nxt.z;
-            nxt = fetch_pos(j + 1);
+            cp_async_wait_all();
+            float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) cur = lds128(pos_s + (j & 1) * (SPA_PROD_THREADS * 16));
+            const float x = cur.x, y = cur.y, z = cur.z;
+            stage_pos(j + 1);
             float ux = (x + a.bound) * a.inv2b, uy = (y + a.bound) * a.inv2b, uz = (z + a.bound) * a.inv2b;
             // out-of-range inputs encode to 0 (gridencoder.cu:110-135): sample the centre, zero the result
             const bool oob = ux < 0 || ux > 1 || uy < 0 || uy > 1 || uz < 0 || uz > 1;
             if (oob) { ux = 0.5f; uy = 0.5f; uz = 0.5f; }
+            if (row == 0 && half < 2) TT_STAMP(0, 2 + half, j, 0);
             mbar_wait(bar_empty + 8 * slot, (n & 1) ^ 1);                 // slot released by the consumer of its previous use
-            uint8_t* F = smem + L::F + slot * SP_TILE_BYTES;
-            // this thread's levels: 4u .. 4u+3 for units u = half and half + 2 (balances the 8-corner coarse levels
-            // and the 4-corner z-dropped fine levels between the two threads of a row)
+            if (row == 0 && half < 2) TT_STAMP(0, 2 + half, j, 1);
+            const uint32_t F = sbase + L::F + slot * SP_TILE_BYTES;
             #pragma unroll 1
-            for (uint32_t b = 0; b < 2; b++) {
-                const uint32_t u = half + 2 * b;
+            for (uint32_t b = 0; b < my_nu; b++) {
+                const uint32_t u = b == 0 ? my_u0 : my_u1;
                 float2 f[4];
                 if ((flat_units >> u) & 1) gather3_dyn4<true>(a.grid, 4 * u, ux, uy, uz, f);
                 else gather3_dyn4<false>(a.grid, 4 * u, ux, uy, uz, f);
                 if (oob) { f[0] = f[1] = f[2] = f[3] = make_float2(0.f, 0.f); }
                 const uint4 hi = make_uint4(pack_h2(f[0].x, f[0].y), pack_h2(f[1].x, f[1].y), pack_h2(f[2].x, f[2].y), pack_h2(f[3].x, f[3].y));
-                *reinterpret_cast<uint4*>(F + sw128(row, u)) = hi;
-                *reinterpret_cast<uint4*>(F + sw128(row, 4 + u)) =
-                    make_uint4(pack_h2(h_resid(f[0].x), h_resid(f[0].y)), pack_h2(h_resid(f[1].x), h_resid(f[1].y)),
-                               pack_h2(h_resid(f[2].x), h_resid(f[2].y)), pack_h2(h_resid(f[3].x), h_resid(f[3].y)));
+                sts128(F + sw128(row, u), hi);
+                sts128(F + sw128(row, 4 + u), make_uint4(pack_h2(h_resid(f[0].x), h_resid(f[0].y)), pack_h2(h_resid(f[1].x), h_resid(f[1].y)),
+                                                         pack_h2(h_resid(f[2].x), h_resid(f[2].y)), pack_h2(h_resid(f[3].x), h_resid(f[3].y))));
                 if (valid) a.io.feat_hi[(size_t)i * 4 + u] = hi;
+                if (row == 0 && half < 2) TT_STAMP(0, 2 + half, j, 2 + b);
+                if (row == 0 && half < 2 && my_nu == 1) TT_STAMP(0, 2 + half, j, 3);
             }
             fence_async_smem();
             mbar_arrive(bar_full + 8 * slot);
+            if (row == 0 && half < 2) TT_STAMP(0, 2 + half, j, 4);
         }
     } else {
         // ------------------------------------------------ consumers ------------------------------------------------
-        const uint32_t stream = (warp - 8) >> 2, row = tid & 127;
-        const uint32_t t_d = tmem_base + (((warp & 3) * 32) << 16) + stream * SP_TM_STREAM;
-        const uint32_t m_d = tmem_base + stream * SP_TM_STREAM;
+        // warp-uniform copies of the warp index and the TMEM base: the tcgen05.mma operands derived from them then live in uniform registers.
+        // Derived from threadIdx / a shared-memory load they were per-thread values, and every MMA was issued through an ELECT / R2UR
+        // broadcast loop of 13 instructions (~75 cycles per MMA on the stream's critical path, longer than the MMA itself).
+        const uint32_t warp_u = __shfl_sync(0xffffffffu, warp, 0), tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t stream = (warp_u - 4 * SPA_PROD_WG) >> 2, row = tid & 127;
+        const uint32_t t_d = tmem_u + (((warp_u & 3) * 32) << 16) + stream * SP_TM_STREAM;
+        const uint32_t m_d = tmem_u + stream * SP_TM_STREAM;
         const uint32_t bar_mma = sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT + stream);
         const uint32_t w_addr = sbase;
-        const bool leader = row == 0;
+        // One elected lane of the stream's first warp waits on / arrives at the ring barriers and issues the MMAs.  The region must be guarded by
+        // a warp-uniform test followed DIRECTLY by elect.sync (the CUTLASS idiom): only then does ptxas know that a single thread runs it and emit
+        // the tcgen05.mma instructions back to back.  Guarded by `threadIdx == x` every MMA was wrapped in an ELECT / R2UR / branch loop of 11-13
+        // instructions (~75 cycles per MMA on the stream's critical path -- longer than the 64 tensor-pipe cycles of the MMA itself).
+        const bool lead_warp = (warp_u & 3) == 0;
         uint32_t phase = 0;
         for (uint32_t j = stream; j < my_tiles; j += 2) {
             const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
@@ -344,8 +414,10 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             const uint32_t f_addr = sbase + L::F + slot * SP_TILE_BYTES;
             tc_fence_before();
             bar_named(1 + stream, 128);                                   // previous tile's accumulator reads are done
-            if (leader) {
+            if (lead_warp && elect_one_sync()) {
+                TT_STAMP(0, stream, j, 0);
                 mbar_wait(bar_full + 8 * slot, n & 1);
+                TT_STAMP(0, stream, j, 1);
                 tc_fence_after();
                 // split precision: F_hi W_hi + F_lo W_hi + F_hi W_lo  (K = 32 each)
                 #pragma unroll
@@ -358,11 +430,14 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             }
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
-            if (leader) mbar_arrive(bar_empty + 8 * slot);                // the feature tile has been consumed
-            epilogue_relu_to_A_n<true, 4>(t_d, t_d + SP_TM_AHI, t_d + SP_TM_ALO, 0, bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);
+            TT_LSTAMP(0, stream, j, 2);
+            if (lead_warp && elect_one_sync()) mbar_arrive(bar_empty + 8 * slot);                // the feature tile has been consumed
+            epilogue_split_to_A_pipe(t_d, t_d + SP_TM_AHI, t_d + SP_TM_ALO, bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);
+            TT_LSTAMP(0, stream, j, 3);
             tc_fence_before();
             bar_named(1 + stream, 128);
-            if (leader) {
+            if (lead_warp && elect_one_sync()) {
+                TT_STAMP(0, stream, j, 4);
                 tc_fence_after();
                 #pragma unroll
                 for (int k = 0; k < 8; k++)
@@ -377,26 +452,38 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_amb(const SpArgs a) {
             }
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
-            // ambient output layer (128 -> 2) in fp32 from the accumulator, weights from the constant bank; tanh
+            TT_LSTAMP(0, stream, j, 5);
+            // ambient output layer (128 -> 2) in fp32 from the accumulator; tanh.  Weights come from shared memory as broadcast LDS.128 (one per
+            // column pair and both outputs): indexing the kernel-parameter copy with the loop variable compiled to 128 LDC.64 per row, and the
+            // constant path's throughput made this phase 2,400 cycles per tile (the longest of the stream's chain; tc_timeline).  The accumulator
+            // load of the next 32 columns is in flight while the current ones are reduced.
             float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;          // (even, odd) column partial sums of the two outputs
-            #pragma unroll 1
-            for (int c = 0; c < 4; c++) {
-                float v[32];
-                tmem_ld32(t_d + 32 * c, v);
-                if (dbg) {
-                    #pragma unroll
-                    for (int q = 0; q < 32; q++) dbg[1 * 128 * 144 + 32 * c + q] = v[q];
-                }
+            {
+                uint32_t r[2][32];
+                tmem_ld32_issue(t_d, r[0]);
+                tmem_wait_ld32(r[0]);
                 #pragma unroll
-                for (int q = 0; q < 32; q += 2) {
-                    const float2 r = make_float2(fmaxf(v[q], 0.f), fmaxf(v[q + 1], 0.f));
-                    acc0 = ffma2(r, make_float2(a.w_amb2[32 * c + q], a.w_amb2[32 * c + q + 1]), acc0);
-                    acc1 = ffma2(r, make_float2(a.w_amb2[128 + 32 * c + q], a.w_amb2[128 + 32 * c + q + 1]), acc1);
+                for (int c = 0; c < 4; c++) {
+                    uint32_t (&v)[32] = r[c & 1];
+                    if (c < 3) tmem_ld32_issue(t_d + 32 * (c + 1), r[(c + 1) & 1]);
+                    if (dbg) {
+                        #pragma unroll
+                        for (int q = 0; q < 32; q++) dbg[1 * 128 * 144 + 32 * c + q] = __uint_as_float(v[q]);
+                    }
+                    #pragma unroll
+                    for (int q = 0; q < 32; q += 2) {
+                        const float4 w = lds128(sbase + L::W2 + 16 * (16 * c + (q >> 1)));
+                        const float2 h = make_float2(fmaxf(__uint_as_float(v[q]), 0.f), fmaxf(__uint_as_float(v[q + 1]), 0.f));
+                        acc0 = ffma2(h, make_float2(w.x, w.y), acc0);
+                        acc1 = ffma2(h, make_float2(w.z, w.w), acc1);
+                    }
+                    if (c < 3) tmem_wait_ld32(r[(c + 1) & 1]);
                 }
             }
             const float s0 = acc0.x + acc0.y, s1 = acc1.x + acc1.y;
             if (dbg) { dbg[2 * 128 * 144 + 0] = s0; dbg[2 * 128 * 144 + 1] = s1; }
             if (i < M) a.io.amb_pos[i] = make_float2(tanhf(s0), tanhf(s1));
+            TT_LSTAMP(0, stream, j, 6);
         }
     }
     tc_fence_before();
@@ -417,8 +504,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
     const uint32_t M = a.io.M_dev ? *a.io.M_dev : a.io.M_host;
     if (M == 0) return;
     const uint32_t cuts[5] = {0, WB2_SIG1, WB2_MRG, WB2_COL1, WB2_TOTAL};
-    const uint32_t tmem_base = sp_setup<WB2_TOTAL>(smem, sbase, a, cuts, 4);
-    const float* bias_ind = reinterpret_cast<const float*>(smem + L::BIAS);
+    const uint32_t tmem_base = sp_setup<WB2_TOTAL>(smem, sbase, a, cuts, 4, 256);
+    const uint32_t bias_ind = sbase + L::BIAS;
     const uint32_t bar_full = sbase + L::BAR + 8, bar_empty = sbase + L::BAR + 8 * (1 + SP_NSLOT);
     const uint32_t num_tiles = (M + 127) / 128;
     const uint32_t my_tiles = num_tiles > blockIdx.x ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -426,59 +513,88 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
     if (warp < 8) {
         // ------------------------------------------------ producers ------------------------------------------------
         const uint32_t half = tid >> 7, row = tid & 127;
-        // per-row inputs of one tile; fetched ONE TILE AHEAD so that their DRAM latency overlaps the previous tile's gathers
-        struct RowIn { uint4 hi0, hi1; float2 ap; float4 dir; };
-        auto fetch = [&](uint32_t j) {
-            RowIn r;
-            r.hi0 = make_uint4(0, 0, 0, 0); r.hi1 = r.hi0; r.ap = make_float2(0.f, 0.f); r.dir = make_float4(0.f, 0.f, 1.f, 0.f);
-            const uint32_t i = (blockIdx.x + j * gridDim.x) * 128 + row;
+        // Per-row inputs of a tile (32 B of position features, the ambient coordinate, the ray's view direction) are staged ONE TILE AHEAD with
+        // cp.async -- the features and the direction straight into the NEXT ring slot, which is therefore acquired one tile early -- and the ray
+        // id TWO tiles ahead, so that the dependent pos4.w -> rays_d chain never sits on a producer's critical path.  (As register prefetches the
+        // loads shared a scoreboard with unrelated instructions and the first use of the current tile's values waited for the next tile's DRAM
+        // access; half 1, which also fetched the direction, had become the kernel's bottleneck: tc_timeline, profiles/r02_summary.md section 7.)
+        const uint32_t ap_s = sbase + L::AP + 8 * tid, ray_s = sbase + L::RAY + 4 * row;
+        auto tile_row = [&](uint32_t j) { return (blockIdx.x + j * gridDim.x) * 128 + row; };
+        auto stage_ray = [&](uint32_t j) {          // half 1, sample-list form only
+            const uint32_t i = tile_row(j);
+            if (half == 1 && a.io.pos4 && j < my_tiles && i < M) cp_async4(ray_s + (j % 3) * 512, reinterpret_cast<const float*>(a.io.pos4 + i) + 3);
+        };
+        auto stage_inputs = [&](uint32_t j) {       // needs: slot of tile j acquired; ray id of tile j staged and complete
+            const uint32_t i = tile_row(j), slot = j % SP_NSLOT;
             if (j < my_tiles && i < M) {
-                r.hi0 = a.io.feat_hi[(size_t)i * 4 + 2 * half];
-                r.hi1 = a.io.feat_hi[(size_t)i * 4 + 2 * half + 1];
-                r.ap = a.io.amb_pos[i];
-                if (half == 1) {          // view direction of the row's ray: fetched here, off the consumers' critical path
-                    if (a.io.pos4) {
-                        const int ray = __float_as_int(a.io.pos4[i].w);
-                        r.dir.x = __ldg(a.io.rays_d + 3 * (size_t)ray); r.dir.y = __ldg(a.io.rays_d + 3 * (size_t)ray + 1); r.dir.z = __ldg(a.io.rays_d + 3 * (size_t)ray + 2);
-                    } else if (a.io.dirs) { r.dir.x = a.io.dirs[3 * (size_t)i]; r.dir.y = a.io.dirs[3 * (size_t)i + 1]; r.dir.z = a.io.dirs[3 * (size_t)i + 2]; }
+                const uint32_t F = sbase + L::F + slot * SP_TILE_BYTES;
+                cp_async16(F + sw128(row, 2 * half), a.io.feat_hi + (size_t)i * 4 + 2 * half);
+                cp_async16(F + sw128(row, 2 * half + 1), a.io.feat_hi + (size_t)i * 4 + 2 * half + 1);
+                cp_async8(ap_s + (j & 1) * 2048, a.io.amb_pos + i);
+                if (half == 1) {
+                    const uint32_t d = sbase + L::DIR + 16 * (slot * 128 + row);
+                    const float* src = nullptr;
+                    if (a.io.pos4) src = a.io.rays_d + 3 * (size_t)lds32(ray_s + (j % 3) * 512);
+                    else if (a.io.dirs) src = a.io.dirs + 3 * (size_t)i;
+                    if (src) { cp_async4(d, src); cp_async4(d + 4, src + 1); cp_async4(d + 8, src + 2); }
+                    else sts128f(d, make_float4(0.f, 0.f, 1.f, 0.f));
                 }
             }
-            return r;
         };
-        RowIn nxt = fetch(0);
+        stage_ray(0);
+        cp_async_commit();
+        cp_async_wait_all();
+        mbar_wait(bar_empty, 1);                      // slot 0 (free at start)
+        stage_inputs(0);
+        stage_ray(1);
+        cp_async_commit();
         #pragma unroll 1
         for (uint32_t j = 0; j < my_tiles; j++) {
-            const uint32_t slot = j % SP_NSLOT, n = j / SP_NSLOT;
-            const RowIn cur = nxt;
-            nxt = fetch(j + 1);
-            const uint4 hi0 = cur.hi0, hi1 = cur.hi1;
-            const float2 ap = cur.ap;
-            const float4 dir = cur.dir;
+            const uint32_t slot = j % SP_NSLOT;
+            const bool valid = tile_row(j) < M;
+            cp_async_wait_all();                      // this tile's staged inputs (issued one tile ago) and the next tile's ray id have landed
+            if (row == 0) TT_STAMP(1, 2 + half, j, 0);
+            if (j + 1 < my_tiles) mbar_wait(bar_empty + 8 * ((j + 1) % SP_NSLOT), (((j + 1) / SP_NSLOT) & 1) ^ 1);   // acquire the NEXT slot
+            if (row == 0) TT_STAMP(1, 2 + half, j, 1);
+            stage_inputs(j + 1);
+            stage_ray(j + 2);
+            cp_async_commit();
+            const uint32_t F = sbase + L::F + slot * SP_TILE_BYTES;
+            float2 ap = make_float2(0.f, 0.f);
+            if (valid) ap = lds64(ap_s + (j & 1) * 2048);
+            else {                                    // rows past the end of the list: defined (zero) operands
+                sts128(F + sw128(row, 2 * half), make_uint4(0, 0, 0, 0));
+                sts128(F + sw128(row, 2 * half + 1), make_uint4(0, 0, 0, 0));
+                if (half == 1) sts128f(sbase + L::DIR + 16 * (slot * 128 + row), make_float4(0.f, 0.f, 1.f, 0.f));
+            }
             const float vx = (ap.x + 1.0f) * 0.5f, vy = (ap.y + 1.0f) * 0.5f;
-            mbar_wait(bar_empty + 8 * slot, (n & 1) ^ 1);
-            uint8_t* F = smem + L::F + slot * SP_TILE_BYTES;
-            *reinterpret_cast<uint4*>(F + sw128(row, 2 * half)) = hi0;
-            *reinterpret_cast<uint4*>(F + sw128(row, 2 * half + 1)) = hi1;
-            if (half == 1) reinterpret_cast<float4*>(smem + L::DIR)[slot * 128 + row] = dir;
             float2 f[8];
             gather2_dyn8(a.grid, 8 * half, vx, vy, f);
             #pragma unroll
             for (int u = 0; u < 2; u++)
-                *reinterpret_cast<uint4*>(F + sw128(row, 4 + 2 * half + u)) =
-                    make_uint4(pack_h2(f[4 * u].x, f[4 * u].y), pack_h2(f[4 * u + 1].x, f[4 * u + 1].y),
-                               pack_h2(f[4 * u + 2].x, f[4 * u + 2].y), pack_h2(f[4 * u + 3].x, f[4 * u + 3].y));
+                sts128(F + sw128(row, 4 + 2 * half + u), make_uint4(pack_h2(f[4 * u].x, f[4 * u].y), pack_h2(f[4 * u + 1].x, f[4 * u + 1].y),
+                                                                    pack_h2(f[4 * u + 2].x, f[4 * u + 2].y), pack_h2(f[4 * u + 3].x, f[4 * u + 3].y)));
             fence_async_smem();
             mbar_arrive(bar_full + 8 * slot);
+            if (row == 0) TT_STAMP(1, 2 + half, j, 2);
         }
     } else {
         // ------------------------------------------------ consumers ------------------------------------------------
-        const uint32_t stream = (warp - 8) >> 2, row = tid & 127;
-        const uint32_t t_d = tmem_base + (((warp & 3) * 32) << 16) + stream * SP_TM_STREAM;
-        const uint32_t m_d = tmem_base + stream * SP_TM_STREAM;
+        // warp-uniform copies of the warp index and the TMEM base: the tcgen05.mma operands derived from them then live in uniform registers.
+        // Derived from threadIdx / a shared-memory load they were per-thread values, and every MMA was issued through an ELECT / R2UR
+        // broadcast loop of 13 instructions (~75 cycles per MMA on the stream's critical path, longer than the MMA itself).
+        const uint32_t warp_u = __shfl_sync(0xffffffffu, warp, 0), tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t stream = (warp_u - 8) >> 2, row = tid & 127;
+        const uint32_t t_d = tmem_u + (((warp_u & 3) * 32) << 16) + stream * SP_TM_STREAM;
+        const uint32_t m_d = tmem_u + stream * SP_TM_STREAM;
         const uint32_t t_a = t_d + SP_TM_A, m_a = m_d + SP_TM_A;
         const uint32_t bar_mma = sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT + stream);
         const uint32_t w_addr = sbase;
-        const bool leader = row == 0;
+        // One elected lane of the stream's first warp waits on / arrives at the ring barriers and issues the MMAs.  The region must be guarded by
+        // a warp-uniform test followed DIRECTLY by elect.sync (the CUTLASS idiom): only then does ptxas know that a single thread runs it and emit
+        // the tcgen05.mma instructions back to back.  Guarded by `threadIdx == x` every MMA was wrapped in an ELECT / R2UR / branch loop of 11-13
+        // instructions (~75 cycles per MMA on the stream's critical path -- longer than the 64 tensor-pipe cycles of the MMA itself).
+        const bool lead_warp = (warp_u & 3) == 0;
         const bool sigma_only = !a.io.out4 && !a.io.rgbs;          // density query (uniform)
         uint32_t phase = 0;
         for (uint32_t j = stream; j < my_tiles; j += 2) {
@@ -486,13 +602,14 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             const uint32_t i = tile * 128 + row;
             const bool valid = i < M;
             float* dbg = (DBG && a.dbg && tile == 0) ? a.dbg + (size_t)row * 144 : nullptr;   // DBG = false: folds every dump away
-            uint8_t* F = smem + L::F + slot * SP_TILE_BYTES;
             const uint32_t f_addr = sbase + L::F + slot * SP_TILE_BYTES;
             tc_fence_before();
             bar_named(1 + stream, 128);
             // ---- sigma layer 0: D = F[:, 0:64] @ Ws0^T ------------------------------------------------------------
-            if (leader) {
+            if (lead_warp && elect_one_sync()) {
+                TT_STAMP(1, stream, j, 0);
                 mbar_wait(bar_full + 8 * slot, n & 1);
+                TT_STAMP(1, stream, j, 1);
                 tc_fence_after();
                 #pragma unroll
                 for (int k = 0; k < 4; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WB2_SIG0 + 32 * k), idesc_f16(128), k);
@@ -500,11 +617,13 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             }
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
-            epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 3 * 128 * 144 : nullptr);
+            TT_LSTAMP(1, stream, j, 2);
+            epilogue_relu_to_A_pipe<false>(t_d, t_a, 0u, dbg ? dbg + 3 * 128 * 144 : nullptr);
+            TT_LSTAMP(1, stream, j, 3);
             tc_fence_before();
             bar_named(1 + stream, 128);
             // ---- sigma layer 1 -----------------------------------------------------------------------------------------
-            if (leader) {
+            if (lead_warp && elect_one_sync()) {
                 tc_fence_after();
                 #pragma unroll
                 for (int k = 0; k < 8; k++)
@@ -513,24 +632,26 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             }
             // SH(dir) -> F[row][k 32..47]: the sigma-layer-0 MMA that read this slot has completed (waited above)
             {
-                const float4 dir = reinterpret_cast<const float4*>(smem + L::DIR)[slot * 128 + row];   // visible: the leader's full-barrier wait + bar.sync
+                const float4 dir = lds128(sbase + L::DIR + 16 * (slot * 128 + row));   // visible: the leader's full-barrier wait + bar.sync
                 float sh[16];
                 sh4(dir.x, dir.y, dir.z, sh);
                 uint32_t p[8];
                 #pragma unroll
                 for (int q = 0; q < 8; q++) p[q] = pack_h2(sh[2 * q], sh[2 * q + 1]);
-                *reinterpret_cast<uint4*>(F + sw128(row, 4)) = make_uint4(p[0], p[1], p[2], p[3]);
-                *reinterpret_cast<uint4*>(F + sw128(row, 5)) = make_uint4(p[4], p[5], p[6], p[7]);
+                sts128(f_addr + sw128(row, 4), make_uint4(p[0], p[1], p[2], p[3]));
+                sts128(f_addr + sw128(row, 5), make_uint4(p[4], p[5], p[6], p[7]));
                 fence_async_smem();
             }
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
-            epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 4 * 128 * 144 : nullptr);
+            TT_LSTAMP(1, stream, j, 4);
+            epilogue_relu_to_A_pipe<false>(t_d, t_a, 0u, dbg ? dbg + 4 * 128 * 144 : nullptr);
+            TT_LSTAMP(1, stream, j, 5);
             tc_fence_before();
             bar_named(1 + stream, 128);
             if (sigma_only) {
                 // density query: only the sigma-logit row block of the merged layer (rows 128..143 of the image, N = 16); no colour net
-                if (leader) {
+                if (lead_warp && elect_one_sync()) {
                     tc_fence_after();
                     #pragma unroll
                     for (int k = 0; k < 8; k++)
@@ -539,7 +660,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                 }
                 stream_wait_mma(bar_mma, phase);
                 tc_fence_after();
-                if (leader) mbar_arrive(bar_empty + 8 * slot);
+                if (lead_warp && elect_one_sync()) mbar_arrive(bar_empty + 8 * slot);
                 float s4[4];
                 tmem_ld4(t_d, s4);
                 if (valid) {
@@ -549,7 +670,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                 continue;
             }
             // ---- merged sigma layer 2 x colour layer 0 (N = 144) + SH part (SS, K = 16, N = 128) --------------------------
-            if (leader) {
+            if (lead_warp && elect_one_sync()) {
                 tc_fence_after();
                 #pragma unroll
                 for (int k = 0; k < 8; k++)
@@ -559,22 +680,24 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
             }
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
-            if (leader) mbar_arrive(bar_empty + 8 * slot);                // last reader of the feature tile is done
+            TT_LSTAMP(1, stream, j, 6);
+            if (lead_warp && elect_one_sync()) mbar_arrive(bar_empty + 8 * slot);                // last reader of the feature tile is done
             float sg[4];
             tmem_ld4(t_d + 128, sg);
             if (dbg) dbg[5 * 128 * 144 + 128] = sg[0];
             if (a.bias) epilogue_relu_to_A_pipe<true>(t_d, t_a, bias_ind, dbg ? dbg + 5 * 128 * 144 : nullptr);
-            else epilogue_relu_to_A_pipe<false>(t_d, t_a, nullptr, dbg ? dbg + 5 * 128 * 144 : nullptr);
+            else epilogue_relu_to_A_pipe<false>(t_d, t_a, 0u, dbg ? dbg + 5 * 128 * 144 : nullptr);
             tc_fence_before();
             bar_named(1 + stream, 128);
             // ---- colour layer 1 (N = 16; 3 real outputs) -> sigmoid ---------------------------------------------------------
-            if (leader) {
+            if (lead_warp && elect_one_sync()) {
                 tc_fence_after();
                 #pragma unroll
                 for (int k = 0; k < 8; k++)
                     mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_COL1 + (k >> 2) * (16 * 128) + 32 * (k & 3)), idesc_f16(16), k);
                 mma_commit(bar_mma);
             }
+            TT_LSTAMP(1, stream, j, 7);
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
             float c[4];
@@ -699,14 +822,14 @@ int field_tc_launch(const GfModel* model, const FieldTcIO& io_in, cudaStream_t s
     a.wimg = (const uint8_t*)model->tc2_blob;
     a.bias = io.bias_amb;
     memcpy(a.w_amb2, model->w_amb2_host, sizeof(a.w_amb2));
-    if (a.dbg) k_tc_amb<true><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
-    else k_tc_amb<false><<<grid, SP_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
+    if (a.dbg && !GF_TC_TIMING) k_tc_amb<true><<<grid, SPA_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
+    else k_tc_amb<false><<<grid, SPA_THREADS, SpSmem<WA_TOTAL>::BYTES, st>>>(a);
     const int rc = check_launch("field_tc_split(amb)");
     if (rc) return rc;
     a.grid = model->dev.amb;
     a.wimg = (const uint8_t*)model->tc2_blob + WA_TOTAL;
     a.bias = model->dev.ind ? model->dev.w + model->dev.c_bind : nullptr;
-    if (a.dbg) k_tc_sigcol<true><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
+    if (a.dbg && !GF_TC_TIMING) k_tc_sigcol<true><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
     else k_tc_sigcol<false><<<grid, SP_THREADS, SpSmem<WB2_TOTAL>::BYTES, st>>>(a);
     return check_launch("field_tc_split(sigcol)");
 }

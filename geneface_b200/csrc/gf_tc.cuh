@@ -67,6 +67,18 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// elect.sync on the full warp (call it convergently, right after a warp-uniform test): true in exactly one lane
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0, lane = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %2;\n\t"
+        "@%%px mov.s32 %1, 1;\n\t"
+        "mov.s32 %0, %%rx;\n\t}"
+        : "+r"(lane), "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -101,6 +113,38 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// explicit shared-space accesses by 32-bit shared address.  The kernels' smem pointer is derived from an aligned-up extern array through integer
+// arithmetic, so plain C++ dereferences compile to GENERIC LD.E / ST.E (address-space check on every access; seen in SASS and as long-scoreboard
+// stalls of the bias loads in the ncu source view, profiles/r02_summary.md section 7); these compile to LDS / STS.
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// per-thread asynchronous global -> shared copies (LDGSTS): completion is tracked by the async-group counter, not by the register scoreboards
+// the compiler shares between unrelated loads
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ float2 lds64(uint32_t saddr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     const __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -126,7 +170,7 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t p) { return __half22float2(
 // SPLIT: also emit the fp16 residual into a second A region (hi + lo ~ 21-bit operand): hi = rz(relu(v)) so that the
 // residual relu(v) - hi is non-negative and a second cvt.relu packs it (a negative v gives hi = 0 and residual v -> 0).
 template <bool SPLIT, int NCHUNK>
-__device__ __forceinline__ void epilogue_relu_to_A_n(uint32_t t_d, uint32_t t_a, uint32_t t_alo, int col0, const float* __restrict__ bias_smem, float* dbg) {
+__device__ __forceinline__ void epilogue_relu_to_A_n(uint32_t t_d, uint32_t t_a, uint32_t t_alo, int col0, uint32_t bias_saddr, float* dbg) {
     #pragma unroll 1
     for (int c = 0; c < NCHUNK; c++) {
         const int col = col0 + 32 * c;
@@ -136,10 +180,10 @@ __device__ __forceinline__ void epilogue_relu_to_A_n(uint32_t t_d, uint32_t t_a,
             #pragma unroll
             for (int i = 0; i < 32; i++) dbg[col + i] = v[i];
         }
-        if (bias_smem) {
+        if (bias_saddr) {
             #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(bias_smem + col + i);
+                const float4 b = lds128(bias_saddr + 4 * (col + i));
                 v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
         }
@@ -189,7 +233,7 @@ __device__ __forceinline__ void tmem_wait_ld32(uint32_t (&r)[32]) {
 // 128 accumulator columns -> (+bias) -> ReLU -> fp16 A operand, software-pipelined: the load of chunk c+1 is in flight while
 // chunk c is converted and stored (this epilogue sits on the consumer streams' critical path).
 template <bool BIAS>
-__device__ __forceinline__ void epilogue_relu_to_A_pipe(uint32_t t_d, uint32_t t_a, const float* __restrict__ bias_smem, float* dbg) {
+__device__ __forceinline__ void epilogue_relu_to_A_pipe(uint32_t t_d, uint32_t t_a, uint32_t bias_saddr, float* dbg) {
     uint32_t r[2][32];
     tmem_ld32_issue(t_d, r[0]);
     tmem_wait_ld32(r[0]);
@@ -203,12 +247,47 @@ __device__ __forceinline__ void epilogue_relu_to_A_pipe(uint32_t t_d, uint32_t t
         }
         uint32_t p[16];
         #pragma unroll
-        for (int i = 0; i < 16; i++) {
+        for (int i = 0; i < 16; i += 2) {
             float v0 = __uint_as_float(cur[2 * i]), v1 = __uint_as_float(cur[2 * i + 1]);
-            if (BIAS) { const float2 b = *reinterpret_cast<const float2*>(bias_smem + 32 * c + 2 * i); v0 += b.x; v1 += b.y; }
+            float v2 = __uint_as_float(cur[2 * i + 2]), v3 = __uint_as_float(cur[2 * i + 3]);
+            if (BIAS) { const float4 b = lds128(bias_saddr + 4 * (32 * c + 2 * i)); v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w; }
             p[i] = pack_relu_h2(v0, v1);
+            p[i + 1] = pack_relu_h2(v2, v3);
         }
         tmem_st16(t_a + 16 * c, p);
+        if (c < 3) tmem_wait_ld32(r[(c + 1) & 1]);
+    }
+    tmem_wait_st();
+}
+
+// split-precision form of the above (ambient layer 0 -> layer 1): + bias, hi = rz(relu(v)), lo = relu(v - hi), both stored as A operands; the
+// accumulator load of chunk c+1 is in flight while chunk c is converted
+__device__ __forceinline__ void epilogue_split_to_A_pipe(uint32_t t_d, uint32_t t_a, uint32_t t_alo, uint32_t bias_saddr, float* dbg) {
+    uint32_t r[2][32];
+    tmem_ld32_issue(t_d, r[0]);
+    tmem_wait_ld32(r[0]);
+    #pragma unroll
+    for (int c = 0; c < 4; c++) {
+        uint32_t (&cur)[32] = r[c & 1];
+        if (c < 3) tmem_ld32_issue(t_d + 32 * (c + 1), r[(c + 1) & 1]);
+        if (dbg) {
+            #pragma unroll
+            for (int i = 0; i < 32; i++) dbg[32 * c + i] = __uint_as_float(cur[i]);
+        }
+        uint32_t p[16], q[16];
+        #pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            const float4 b = lds128(bias_saddr + 4 * (32 * c + 2 * i));
+            const float v0 = __uint_as_float(cur[2 * i]) + b.x, v1 = __uint_as_float(cur[2 * i + 1]) + b.y;
+            const float v2 = __uint_as_float(cur[2 * i + 2]) + b.z, v3 = __uint_as_float(cur[2 * i + 3]) + b.w;
+            p[i] = pack_relu_rz_h2(v0, v1);
+            p[i + 1] = pack_relu_rz_h2(v2, v3);
+            const float2 h0 = unpack_h2(p[i]), h1 = unpack_h2(p[i + 1]);
+            q[i] = pack_relu_h2(v0 - h0.x, v1 - h0.y);
+            q[i + 1] = pack_relu_h2(v2 - h1.x, v3 - h1.y);
+        }
+        tmem_st16(t_a + 16 * c, p);
+        tmem_st16(t_alo + 16 * c, q);
         if (c < 3) tmem_wait_ld32(r[(c + 1) & 1]);
     }
     tmem_wait_st();
