@@ -693,6 +693,10 @@ def run_train(args, rank, world, local):
     import bench_train
     line = bench_train.run(steps=args.steps, warmup=args.warmup, local=local)
     line["amp"] = bench_train.run(steps=args.steps, warmup=args.warmup, local=local, amp=True)
+    # the MLPs on the gf_tl_* tcgen05 operators (fp16 operands, fp32 accumulation: the arithmetic of the amp arm) -- BASELINE.json's 4096 rays and the
+    # May configuration's own training batch (n_rays = 65536)
+    line["tc_mlp"] = bench_train.run(steps=args.steps, warmup=args.warmup, local=local, mlp="tc", no_ref=True)
+    line["tc_mlp_65536"] = bench_train.run(steps=max(5, args.steps // 2), warmup=args.warmup, local=local, rays=65536, mlp="tc", no_ref=True)
     print(json.dumps(line), flush=True)
 
 

@@ -18,7 +18,7 @@ _SO = os.environ.get("GF_LIBGFRENDER") or os.path.join(_PKG, "libgfrender.so")
 _VARIANT = bool(os.environ.get("GF_LIBGFRENDER"))
 _INCLUDE = os.path.join(os.path.dirname(_PKG), "include")
 
-SOURCES = ["api.cu", "raymarch_ops.cu", "encoders.cu", "render_fused.cu", "field_tc_split.cu", "adnerf_ops.cu", "adnerf_mlp_tc.cu"]
+SOURCES = ["api.cu", "raymarch_ops.cu", "encoders.cu", "render_fused.cu", "field_tc_split.cu", "adnerf_ops.cu", "adnerf_mlp_tc.cu", "train_linear_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -125,6 +125,11 @@ _SIGS = {
     "gf_adnerf_mlp_destroy": [c_vp],
     "gf_adnerf_mlp_workspace_bytes": [c_vp, c_u32],
     "gf_adnerf_mlp_forward": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_vp, c_vp, c_u64, c_vp],
+    "gf_tl_tiles_bytes": [c_u32, c_u32],
+    "gf_tl_pack": [c_vp, c_int, c_u32, c_u32, c_u32, c_u32, c_vp, c_vp, c_vp],
+    "gf_tl_weight_image": [c_vp, c_u32, c_u32, c_u32, c_u32, c_vp, c_vp],
+    "gf_tl_gemm": [c_vp, c_u32, c_vp, c_u32, c_u32, c_int, c_u32, c_vp, c_u32, c_int, c_vp, c_u32, c_vp, c_u32, c_u32, c_vp, c_vp],
+    "gf_tl_wgrad": [c_vp, c_u32, c_u32, c_vp, c_u32, c_u32, c_u32, c_vp, c_u32, c_u32, c_u32, c_int, c_vp, c_vp],
     "gf_model_create": [c_vp, c_vp, c_vp],
     "gf_model_destroy": [c_vp],
     "gf_model_packed_bytes": [c_vp],
@@ -142,7 +147,7 @@ _SIGS = {
 }
 _RESTYPE = {"gf_last_error": ctypes.c_char_p, "gf_model_destroy": None, "gf_model_packed_bytes": c_u64,
             "gf_render_workspace_bytes": c_u64, "gf_field_workspace_bytes": c_u64, "gf_adnerf_mlp_workspace_bytes": c_u64,
-            "gf_adnerf_mlp_destroy": None}
+            "gf_adnerf_mlp_destroy": None, "gf_tl_tiles_bytes": ctypes.c_size_t}
 
 EXPORTS = sorted(_SIGS)
 
@@ -166,6 +171,8 @@ def lib():
         try:
             fn = getattr(L, name)
         except AttributeError:
+            if _VARIANT:          # an experiment build of an older source state (A/B runs): the missing operator simply cannot be called
+                continue
             raise RuntimeError("libgfrender.so does not export %s" % name)
         fn.argtypes = argtypes
         fn.restype = _RESTYPE.get(name, ctypes.c_int)

@@ -58,7 +58,19 @@ class MLP(nn.Module):
             nn.Linear(dim_in if l == 0 else dim_hidden, dim_out if l == num_layers - 1 else dim_hidden, bias=False)
             for l in range(num_layers)])
 
+    # 'tc': in training (grad enabled) run forward / grad_input / grad_weight on the gf_tl_* tcgen05 operators (tc_linear.py; fp16 operands, fp32
+    # accumulation = the reference's `amp: true` arithmetic) when the layer widths are inside their envelope; 'torch': library GEMMs under autograd.
+    # Set per model from hparams['train_mlp_backend'] (default: the GF_TRAIN_MLP environment variable, else 'torch').
+    backend = 'torch'
+
+    def _dims(self):
+        return [self.dim_in] + [self.dim_hidden] * (self.num_layers - 1) + [self.dim_out]
+
     def forward(self, x):
+        if self.backend == 'tc' and x.is_cuda and torch.is_grad_enabled() and x.dim() == 2:
+            from . import tc_linear
+            if tc_linear.supported(self._dims()):
+                return tc_linear.tc_mlp(x, [layer.weight for layer in self.net])
         for l, layer in enumerate(self.net):
             x = layer(x)
             if l != self.num_layers - 1:

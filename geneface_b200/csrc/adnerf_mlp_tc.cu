@@ -72,11 +72,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const DenseArgs a) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(smem + (tmem_slot - sbase));
+    // warp-uniform copies (see field_tc_split.cu): with per-thread values every tcgen05.mma went through an ELECT / R2UR broadcast loop
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(smem + (tmem_slot - sbase)), 0);
+    const uint32_t warp_u = __shfl_sync(0xffffffffu, warp, 0);
 
-    if (warp == 0) {
+    if (warp_u == 0) {
         // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_expect_tx(bar_w, nk * wchunk);
             for (uint32_t c = 0; c < nk; c++) bulk_g2s(sbase + W_OFF + c * wchunk, a.w_img + (size_t)c * wchunk, wchunk, bar_w);
             uint32_t it = 0;
@@ -91,9 +93,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const DenseArgs a) {
                 }
             }
         }
-    } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+    } else if (warp_u == 1) {
+        // ---------------------------------------------------------------- MMA issuer (one elected lane; elect.sync directly after the uniform test)
+        if (elect_one_sync()) {
             mbar_wait(bar_w, 0);
             const uint32_t idesc = idesc_f16(a.N);
             uint32_t it = 0;

@@ -191,10 +191,16 @@ __global__ void __launch_bounds__(256) k_grid_forward(const float* __restrict__ 
 //   * when EVERY lane of a warp targets the same entry -- samples of one ray inside one coarse cell, or ambient coordinates clustered in a
 //     few cells of the 2-D grid: the dominant pattern behind the measured contention -- the warp tree-reduces the 32 contributions with
 //     shuffles and commits once instead of serialising 32 same-address reductions;
+//   * LARGER LEVELS OF THE 2-D GRIDS (ambient / torso: the coordinates are network outputs and cluster -- a whole batch can sit in a handful of
+//     cells of every level, so the per-warp commits above still serialise on a few addresses; measured: 37 % of a 65,536-ray step): `cache_ctas`
+//     CTAs per level accumulate through a direct-mapped shared-memory cache (8,192 slots: tag + C floats; a slot is claimed with one atomicCAS,
+//     a conflicting entry goes straight to global memory) and flush the claimed slots once at the end;
 //   * everything else is one 8-byte vector reduction per channel pair (RED.E.ADD.F32x2 / .F16x2) per corner.
 // The sum order differs from the reference's (which is itself non-deterministic: atomics); parity is checked against an fp64
 // re-accumulation.  Measured (profiles/r02_summary.md): 65,536-ray step 25.1 ms (plain reductions) -> 17.9 (privatised) -> 16.0 (+ warp
 // aggregation); at 4,096 rays privatisation loses, so it is switched on from 131,072 samples.
+constexpr uint32_t GRID_BWD_PRIV_BYTES = 13824 * 8;           // 3-D level 1 of the May configuration (C = 2): 110,592 B, 2 CTAs / SM
+constexpr uint32_t GRID_BWD_CACHE_LOG2 = 13, GRID_BWD_CACHE_SLOTS = 1u << GRID_BWD_CACHE_LOG2;   // tags 32 KB + values C x 32 KB
 template <int C, typename Commit>
 __device__ __forceinline__ void grid_update(uint32_t e, float (&v)[C], Commit&& commit) {
     if (__activemask() == 0xffffffffu && __match_any_sync(0xffffffffu, e) == 0xffffffffu) {
@@ -228,13 +234,25 @@ template <typename T, int D, int C>
 __global__ void __launch_bounds__(256) k_grid_backward_b200(const T* __restrict__ grad, const float* __restrict__ inputs,
                                                              const int* __restrict__ offsets, T* __restrict__ grad_grid_all, uint32_t B,
                                                              uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
-                                                             uint32_t interp, uint32_t priv_ctas, uint32_t priv_entries) {
-    extern __shared__ float tab[];                        // private copy of a small level: [hashmap_size][C] fp32
+                                                             uint32_t interp, uint32_t priv_ctas, uint32_t priv_entries, uint32_t cache_ctas) {
+    extern __shared__ float tab[];                        // private copy of a small level: [hashmap_size][C] fp32; or the cache: tags, then values
     const uint32_t level = blockIdx.y;
     const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
     const bool priv = hashmap_size <= priv_entries;
+    const bool cached = !priv && cache_ctas != 0;
     if (priv && blockIdx.x >= priv_ctas) return;
-    const uint32_t nctas = priv ? (priv_ctas < gridDim.x ? priv_ctas : gridDim.x) : gridDim.x;
+    if (cached && blockIdx.x >= cache_ctas) return;
+    const uint32_t nctas = priv ? (priv_ctas < gridDim.x ? priv_ctas : gridDim.x) : cached ? (cache_ctas < gridDim.x ? cache_ctas : gridDim.x) : gridDim.x;
+    uint32_t* ctag = reinterpret_cast<uint32_t*>(tab);
+    float* cval = tab + GRID_BWD_CACHE_SLOTS;
+    if (cached) {
+        for (uint32_t e = threadIdx.x; e < GRID_BWD_CACHE_SLOTS; e += blockDim.x) {
+            ctag[e] = 0xffffffffu;
+            #pragma unroll
+            for (int c = 0; c < C; c++) cval[(size_t)e * C + c] = 0.f;
+        }
+        __syncthreads();
+    }
     T* grad_grid = grad_grid_all + (size_t)(uint32_t)offsets[level] * C;
     float scale; uint32_t resolution;
     level_geometry(level, S, H, scale, resolution);
@@ -279,6 +297,17 @@ __global__ void __launch_bounds__(256) k_grid_backward_b200(const T* __restrict_
                     #pragma unroll
                     for (int c = 0; c < C; c++) atomicAdd(&tab[(size_t)ee * C + c], vv[c]);
                 });
+            } else if (cached) {
+                grid_update<C>(e, v, [&](uint32_t ee, const float (&vv)[C]) {
+                    const uint32_t slot = (ee * 2654435761u) >> (32 - GRID_BWD_CACHE_LOG2);
+                    const uint32_t old = atomicCAS(&ctag[slot], 0xffffffffu, ee);
+                    if (old == 0xffffffffu || old == ee) {
+                        #pragma unroll
+                        for (int c = 0; c < C; c++) atomicAdd(&cval[(size_t)slot * C + c], vv[c]);
+                    } else {
+                        grid_reduce_global<T, C>(grad_grid, ee, vv);
+                    }
+                });
             } else {
                 grid_update<C>(e, v, [&](uint32_t ee, const float (&vv)[C]) { grid_reduce_global<T, C>(grad_grid, ee, vv); });
             }
@@ -294,13 +323,23 @@ __global__ void __launch_bounds__(256) k_grid_backward_b200(const T* __restrict_
             if (any) grid_reduce_global<T, C>(grad_grid, e, v);
         }
     }
+    if (cached) {
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < GRID_BWD_CACHE_SLOTS; e += blockDim.x) {
+            const uint32_t ee = ctag[e];
+            if (ee == 0xffffffffu) continue;
+            float v[C];
+            #pragma unroll
+            for (int c = 0; c < C; c++) v[c] = cval[(size_t)e * C + c];
+            grid_reduce_global<T, C>(grad_grid, ee, v);
+        }
+    }
 }
 
-constexpr uint32_t GRID_BWD_PRIV_BYTES = 13824 * 8;           // 3-D level 1 of the May configuration (C = 2): 110,592 B, 2 CTAs / SM
 
 // GF_GRID_BWD=plain forces plain vector reductions (no privatisation), GF_GRID_BWD=priv forces privatisation at any batch size: A/B runs
 static int grid_bwd_mode() {
-    static const int v = [] { const char* e = getenv("GF_GRID_BWD"); return !e ? 0 : (!strcmp(e, "plain") || !strcmp(e, "legacy")) ? 1 : !strcmp(e, "priv") ? 2 : 0; }();
+    static const int v = [] { const char* e = getenv("GF_GRID_BWD"); return !e ? 0 : (!strcmp(e, "plain") || !strcmp(e, "legacy")) ? 1 : !strcmp(e, "priv") ? 2 : !strcmp(e, "nocache") ? 3 : 0; }();
     return v;
 }
 
@@ -394,14 +433,19 @@ static int launch_grid_backward(const void* grad, const float* inputs, const int
     // Privatisation pays only when the batch is large enough that (a) contention on the small levels is real and (b) every privatising
     // CTA still sees thousands of samples (zero + flush cost one pass over the level's table each).
     const int mode = grid_bwd_mode();
-    const bool use_priv = mode == 2 || (mode == 0 && B >= 131072);
+    const bool use_priv = mode == 2 || ((mode == 0 || mode == 3) && B >= 131072);
+    // the shared-memory cache for the larger levels: 2-D grids only (clustered network-output coordinates), batches large enough to fill the CTAs
+    static_assert((1 + C) * GRID_BWD_CACHE_SLOTS * 4 <= GRID_BWD_PRIV_BYTES || C > 2, "cache does not fit");
+    uint32_t cache_ctas = 0;
+    if (D == 2 && C <= 2 && (mode == 2 || (mode == 0 && B >= 65536))) { cache_ctas = B / 2048; cache_ctas = cache_ctas < 8 ? 8 : (cache_ctas > 128 ? 128 : cache_ctas); }
     uint32_t priv_ctas = B / 4096;
     priv_ctas = priv_ctas < 8 ? 8 : (priv_ctas > 64 ? 64 : priv_ctas);
     uint32_t gx = div_up(B, 256 * 4);
     gx = gx < priv_ctas ? priv_ctas : (gx > 1024 ? 1024 : gx);
+    if (gx < cache_ctas) gx = cache_ctas;
     k_grid_backward_b200<T, D, C><<<dim3(gx, L, 1), 256, GRID_BWD_PRIV_BYTES, st>>>(
         (const T*)grad, inputs, offsets, (T*)grad_emb, B, L, S, H, gridtype, ac, interp, priv_ctas,
-        use_priv ? GRID_BWD_PRIV_BYTES / (uint32_t)(C * sizeof(float)) : 0u);
+        use_priv ? GRID_BWD_PRIV_BYTES / (uint32_t)(C * sizeof(float)) : 0u, cache_ctas);
     int rc = check_launch("grid_encode_backward");
     if (rc) return rc;
     if (dy_dx && grad_inputs) {

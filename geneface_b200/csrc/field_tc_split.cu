@@ -73,7 +73,7 @@ struct SpSmem {
     static constexpr uint32_t POS = W2 + 1024;
     static constexpr uint32_t AP = POS, RAY = POS + 2 * 256 * 8;
     static constexpr uint32_t BAR = POS + 2 * 384 * 16;              // wbar, full[NSLOT], empty[NSLOT], mma[2]
-    static constexpr uint32_t TMEM = BAR + 8 * (1 + 2 * SP_NSLOT + 2);
+    static constexpr uint32_t TMEM = BAR + 8 * (1 + 2 * SP_NSLOT + 4);   // barriers: wbar, full[NSLOT], empty[NSLOT], mma[2], early-layer-0[2]
     static constexpr uint32_t TOTAL = TMEM + 16;
     static constexpr uint32_t BYTES = TOTAL + 1024;
 };
@@ -168,8 +168,7 @@ __device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, cons
             mbar_init(sbase + L::BAR + 8 * (1 + s), nprod);             // full: every producer thread arrives
             mbar_init(sbase + L::BAR + 8 * (1 + SP_NSLOT + s), 1);      // empty: the stream leader arrives
         }
-        mbar_init(sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT), 1);
-        mbar_init(sbase + L::BAR + 8 * (2 + 2 * SP_NSLOT), 1);
+        for (int s = 0; s < 4; s++) mbar_init(sbase + L::BAR + 8 * (1 + 2 * SP_NSLOT + s), 1);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(sbase + L::TMEM, 512);
@@ -371,6 +370,7 @@ __global__ void __launch_bounds__(SPA_THREADS, 1) k_tc_amb(const SpArgs a) {
             mbar_wait(bar_empty + 8 * slot, (n & 1) ^ 1);                 // slot released by the consumer of its previous use
             if (row == 0 && half < 2) TT_STAMP(0, 2 + half, j, 1);
             const uint32_t F = sbase + L::F + slot * SP_TILE_BYTES;
+            uint4 keep0 = make_uint4(0, 0, 0, 0), keep1 = keep0;
             #pragma unroll 1
             for (uint32_t b = 0; b < my_nu; b++) {
                 const uint32_t u = b == 0 ? my_u0 : my_u1;
@@ -382,12 +382,18 @@ __global__ void __launch_bounds__(SPA_THREADS, 1) k_tc_amb(const SpArgs a) {
                 sts128(F + sw128(row, u), hi);
                 sts128(F + sw128(row, 4 + u), make_uint4(pack_h2(h_resid(f[0].x), h_resid(f[0].y)), pack_h2(h_resid(f[1].x), h_resid(f[1].y)),
                                                          pack_h2(h_resid(f[2].x), h_resid(f[2].y)), pack_h2(h_resid(f[3].x), h_resid(f[3].y))));
-                if (valid) a.io.feat_hi[(size_t)i * 4 + u] = hi;
+                if (b == 0) keep0 = hi; else keep1 = hi;
                 if (row == 0 && half < 2) TT_STAMP(0, 2 + half, j, 2 + b);
                 if (row == 0 && half < 2 && my_nu == 1) TT_STAMP(0, 2 + half, j, 3);
             }
             fence_async_smem();
             mbar_arrive(bar_full + 8 * slot);
+            // the fp16 features for kernel B go to HBM AFTER the hand-off: fence.proxy.async is a MEMBAR.ALL.CTA in SASS and would otherwise wait
+            // for these global stores to be acknowledged before the tile can be handed to the consumers
+            if (valid) {
+                a.io.feat_hi[(size_t)i * 4 + my_u0] = keep0;
+                if (my_nu == 2) a.io.feat_hi[(size_t)i * 4 + my_u1] = keep1;
+            }
             if (row == 0 && half < 2) TT_STAMP(0, 2 + half, j, 4);
         }
     } else {
@@ -596,26 +602,31 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
         // instructions (~75 cycles per MMA on the stream's critical path -- longer than the 64 tensor-pipe cycles of the MMA itself).
         const bool lead_warp = (warp_u & 3) == 0;
         const bool sigma_only = !a.io.out4 && !a.io.rgbs;          // density query (uniform)
-        uint32_t phase = 0;
+        // Software pipelining across a stream's tiles: sigma layer 0 of the NEXT tile (an SS MMA: needs only that tile's feature slot and accumulator
+        // columns 0..127, which nobody reads once the last activation epilogue of the current tile has passed its barrier) is issued right behind the
+        // current tile's last MMAs, which therefore write columns 128..143.  It runs while the threads finish the current tile (exp / sigmoid / store),
+        // so the layer's issue -> commit -> wake-up latency (~800 of the stream's ~7,500 cycles per tile, tc_timeline) leaves the chain.
+        const uint32_t bar_s0 = sbase + L::BAR + 8 * (3 + 2 * SP_NSLOT + stream);
+        auto issue_sig0 = [&](uint32_t jj) {                          // called by the elected lane only
+            const uint32_t sl = jj % SP_NSLOT, fa = sbase + L::F + sl * SP_TILE_BYTES;
+            mbar_wait(bar_full + 8 * sl, (jj / SP_NSLOT) & 1);
+            tc_fence_after();
+            #pragma unroll
+            for (int k = 0; k < 4; k++) mma_ss(m_d, smem_desc(fa + 32 * k), smem_desc(w_addr + WB2_SIG0 + 32 * k), idesc_f16(128), k);
+            mma_commit(bar_s0);
+        };
+        uint32_t phase = 0, phase0 = 0;
+        if (stream < my_tiles && lead_warp && elect_one_sync()) issue_sig0(stream);
         for (uint32_t j = stream; j < my_tiles; j += 2) {
-            const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT, n = j / SP_NSLOT;
+            const uint32_t tile = blockIdx.x + j * gridDim.x, slot = j % SP_NSLOT;
             const uint32_t i = tile * 128 + row;
             const bool valid = i < M;
             float* dbg = (DBG && a.dbg && tile == 0) ? a.dbg + (size_t)row * 144 : nullptr;   // DBG = false: folds every dump away
             const uint32_t f_addr = sbase + L::F + slot * SP_TILE_BYTES;
-            tc_fence_before();
-            bar_named(1 + stream, 128);
-            // ---- sigma layer 0: D = F[:, 0:64] @ Ws0^T ------------------------------------------------------------
-            if (lead_warp && elect_one_sync()) {
-                TT_STAMP(1, stream, j, 0);
-                mbar_wait(bar_full + 8 * slot, n & 1);
-                TT_STAMP(1, stream, j, 1);
-                tc_fence_after();
-                #pragma unroll
-                for (int k = 0; k < 4; k++) mma_ss(m_d, smem_desc(f_addr + 32 * k), smem_desc(w_addr + WB2_SIG0 + 32 * k), idesc_f16(128), k);
-                mma_commit(bar_mma);
-            }
-            stream_wait_mma(bar_mma, phase);
+            // ---- sigma layer 0: D = F[:, 0:64] @ Ws0^T (issued one tile ahead) -------------------------------------------
+            TT_LSTAMP(1, stream, j, 0);
+            TT_LSTAMP(1, stream, j, 1);
+            stream_wait_mma(bar_s0, phase0);
             tc_fence_after();
             TT_LSTAMP(1, stream, j, 2);
             epilogue_relu_to_A_pipe<false>(t_d, t_a, 0u, dbg ? dbg + 3 * 128 * 144 : nullptr);
@@ -655,14 +666,15 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                     tc_fence_after();
                     #pragma unroll
                     for (int k = 0; k < 8; k++)
-                        mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_MRG + (k >> 2) * (144 * 128) + 128 * 128 + 32 * (k & 3)), idesc_f16(16), k);
+                        mma_ts(m_d + 128, m_a + 8 * k, smem_desc(w_addr + WB2_MRG + (k >> 2) * (144 * 128) + 128 * 128 + 32 * (k & 3)), idesc_f16(16), k);
                     mma_commit(bar_mma);
+                    mbar_arrive(bar_empty + 8 * slot);          // sigma layer 0 (waited above) was the slot's only reader in this mode
+                    if (j + 2 < my_tiles) issue_sig0(j + 2);
                 }
                 stream_wait_mma(bar_mma, phase);
                 tc_fence_after();
-                if (lead_warp && elect_one_sync()) mbar_arrive(bar_empty + 8 * slot);
                 float s4[4];
-                tmem_ld4(t_d, s4);
+                tmem_ld4(t_d + 128, s4);
                 if (valid) {
                     a.io.sigmas[i] = __expf(s4[0]);
                     if (a.io.ambient) { const float2 ap = a.io.amb_pos[i]; a.io.ambient[2 * (size_t)i] = ap.x; a.io.ambient[2 * (size_t)i + 1] = ap.y; }
@@ -694,14 +706,15 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_tc_sigcol(const SpArgs a) {
                 tc_fence_after();
                 #pragma unroll
                 for (int k = 0; k < 8; k++)
-                    mma_ts(m_d, m_a + 8 * k, smem_desc(w_addr + WB2_COL1 + (k >> 2) * (16 * 128) + 32 * (k & 3)), idesc_f16(16), k);
+                    mma_ts(m_d + 128, m_a + 8 * k, smem_desc(w_addr + WB2_COL1 + (k >> 2) * (16 * 128) + 32 * (k & 3)), idesc_f16(16), k);
                 mma_commit(bar_mma);
+                if (j + 2 < my_tiles) issue_sig0(j + 2);
             }
             TT_LSTAMP(1, stream, j, 7);
             stream_wait_mma(bar_mma, phase);
             tc_fence_after();
             float c[4];
-            tmem_ld4(t_d, c);
+            tmem_ld4(t_d + 128, c);
             if (dbg) { dbg[6 * 128 * 144 + 0] = c[0]; dbg[6 * 128 * 144 + 1] = c[1]; dbg[6 * 128 * 144 + 2] = c[2]; }
             if (valid) {
                 const float sigma = __expf(sg[0]);

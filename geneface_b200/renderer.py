@@ -14,6 +14,7 @@ There is no CPU path: tensors must be CUDA and libgfrender.so must load.
 """
 import ctypes
 import math
+import os
 import random
 
 import numpy as np
@@ -464,6 +465,10 @@ class RADNeRF(NeRFRenderer):
         self.hidden_dim_color = hparams['hidden_dim_color']
         self.direction_embedder, self.direction_embedding_dim = get_encoder('spherical_harmonics')
         self.color_net = MLP(self.direction_embedding_dim + self.geo_feat_dim + self.individual_embedding_dim, 3, self.hidden_dim_color, self.num_layers_color)
+        # training-time MLP backend (cond_encoder.MLP.backend): 'tc' = the gf_tl_* tcgen05 operators, 'torch' = library GEMMs under autograd
+        backend = hparams.get('train_mlp_backend', os.environ.get('GF_TRAIN_MLP', 'torch'))
+        for net in (self.ambient_net, self.sigma_net, self.color_net):
+            net.backend = backend
 
     def cal_cond_feat(self, cond):
         cond_feat = self.cond_prenet(cond)

@@ -1,0 +1,132 @@
+"""Tensor-core MLP for the training step: forward, grad_input and grad_weight of the reference's bias-free MLP
+(modules/radnerfs/cond_encoder.py:92-111: Linear(bias=False) -> ReLU -> ... -> Linear; used by radnerf.py:73-105) on the
+`gf_tl_*` tcgen05 operators of libgfrender (csrc/train_linear_tc.cu) instead of library GEMMs under autograd.
+
+Arithmetic: fp16 operands, fp32 accumulation, fp32 weights and gradients -- what `torch.autocast(float16)` gives the reference under its
+default `amp: true`; the incoming gradient is scaled by a power of two chosen on the device (largest |dy| -> ~2^8) before it is rounded to
+fp16 and the factor is divided out of grad_input / grad_weight in their fp32 epilogues, so the result does not depend on an outer GradScaler.
+
+Envelope: hidden width 128 (the tensor-core tile height of the weight-gradient product), 2 or more layers, input / output widths <= 256 / 144.
+`supported(mlp)` says whether an `MLP` module is inside it; outside it `MLP.forward` keeps the library path.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def _chunks(k):
+    return (k + 63) // 64
+
+
+def _pad16(n):
+    return (n + 15) // 16 * 16
+
+
+def supported(dims):
+    """dims = [in, hidden, ..., hidden, out]"""
+    if len(dims) < 3:
+        return False
+    return all(h == 128 for h in dims[1:-1]) and dims[0] <= 256 and dims[-1] <= 144
+
+
+def _tiles(M, chunks, device):
+    return torch.empty(int(_lib.lib().gf_tl_tiles_bytes(M, chunks)), dtype=torch.uint8, device=device)
+
+
+def _pack(src, K, chunks, scale=None):
+    M = src.shape[0]
+    out = _tiles(M, chunks, src.device)
+    check(_lib.lib().gf_tl_pack(ptr(src), 1 if src.dtype == torch.float16 else 0, src.stride(0), K, M, chunks, ptr(scale), ptr(out), stream_ptr()), "gf_tl_pack")
+    return out
+
+
+def _image(W):
+    N, K = W.shape
+    rows, chunks = _pad16(N), _chunks(K)
+    img = torch.empty(rows * chunks * 128, dtype=torch.uint8, device=W.device)
+    check(_lib.lib().gf_tl_weight_image(ptr(W), N, K, rows, chunks, ptr(img), stream_ptr()), "gf_tl_weight_image")
+    return img, rows, chunks
+
+
+class TcMLPFunction(torch.autograd.Function):
+    """y = W_L relu(... relu(W_0 x)); x [M, K0] fp32 or fp16, W_l fp32 [N_l, K_l]; y [M, N_L] fp32."""
+
+    @staticmethod
+    def forward(ctx, x, *weights):
+        _lib.require_cuda()
+        L = _lib.lib()
+        x = x.detach()
+        if x.dtype not in (torch.float32, torch.float16):
+            x = x.float()
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        ws = [w.detach().float().contiguous() for w in weights]
+        M, K0 = x.shape
+        dims = [K0] + [w.shape[0] for w in ws]
+        assert supported(dims), "TcMLPFunction: layer widths outside the tensor-core envelope"
+        acts = [_pack(x, K0, _chunks(K0))]                     # tile-major fp16 inputs of every layer (saved for backward)
+        imgs = []
+        y = torch.empty(M, dims[-1], dtype=torch.float32, device=x.device)
+        for l, w in enumerate(ws):
+            img, rows, chunks = _image(w)
+            imgs.append((img, rows, chunks))
+            last = l == len(ws) - 1
+            if last:
+                check(L.gf_tl_gemm(ptr(acts[l]), chunks, ptr(img), rows, chunks, 0, M, None, 0, 0, None, 0, ptr(y), y.stride(0), dims[-1], None, stream_ptr()),
+                      "gf_tl_gemm(forward, output layer)")
+            else:
+                h = _tiles(M, 2, x.device)
+                check(L.gf_tl_gemm(ptr(acts[l]), chunks, ptr(img), rows, chunks, 0, M, ptr(h), 2, 1, None, 0, None, 0, 0, None, stream_ptr()), "gf_tl_gemm(forward)")
+                acts.append(h)
+        ctx.acts, ctx.imgs, ctx.dims, ctx.M = acts, imgs, dims, M
+        ctx.x_grad = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        acts, imgs, dims, M = ctx.acts, ctx.imgs, ctx.dims, ctx.M
+        nl = len(imgs)
+        dev = dy.device
+        dy = dy.detach()
+        if dy.dtype not in (torch.float32, torch.float16):
+            dy = dy.float()
+        if dy.stride(-1) != 1:
+            dy = dy.contiguous()
+        # power-of-two scale: largest |dy| -> about 2^8 (head-room for the growth through the layers before fp16 overflows at 2^16); on the device
+        amax = dy.abs().amax().float().clamp_min(1e-30)
+        scale = torch.exp2(torch.floor(8.0 - torch.log2(amax))).clamp(2.0 ** -20, 2.0 ** 40).reshape(1).contiguous()
+        inv = (1.0 / scale).contiguous()
+        n_out = dims[-1]
+        g = _pack(dy, n_out, _chunks(_pad16(n_out)), scale)              # dY tiles (scaled)
+        g_chunks = _chunks(_pad16(n_out))
+        grads_w = [None] * nl
+        dx = None
+        for l in range(nl - 1, -1, -1):
+            img, rows, chunks = imgs[l]
+            N_l, K_l = dims[l + 1], dims[l]
+            dw = torch.zeros(N_l, K_l, dtype=torch.float32, device=dev)
+            if l == nl - 1:
+                # output layer: M side = its 128-wide input activation, N side = dY (padded to 16): D = dW^T
+                check(L.gf_tl_wgrad(ptr(acts[l]), 2, 0, ptr(g), g_chunks, rows, M, ptr(dw), K_l, K_l, N_l, 1, ptr(inv), stream_ptr()), "gf_tl_wgrad(output layer)")
+            else:
+                # M side = this layer's (128-wide) output gradient, N side = its input (padded to whole chunks): D = dW
+                check(L.gf_tl_wgrad(ptr(g), 2, 0, ptr(acts[l]), chunks, min(_pad16(K_l), 64 * chunks), M, ptr(dw), K_l, N_l, K_l, 0, ptr(inv), stream_ptr()), "gf_tl_wgrad")
+            grads_w[l] = dw
+            if l > 0:
+                gn = _tiles(M, 2, dev)
+                check(L.gf_tl_gemm(ptr(g), g_chunks, ptr(img), rows, chunks, 1, M, ptr(gn), 2, 0, ptr(acts[l]), 2, None, 0, 0, None, stream_ptr()), "gf_tl_gemm(dgrad)")
+                g, g_chunks = gn, 2
+            elif ctx.needs_input_grad[0]:
+                dx = torch.empty(M, K_l, dtype=torch.float32, device=dev)
+                check(L.gf_tl_gemm(ptr(g), g_chunks, ptr(img), rows, chunks, 1, M, None, 0, 0, None, 0, ptr(dx), K_l, K_l, ptr(inv), stream_ptr()), "gf_tl_gemm(grad_input)")
+                if ctx.x_grad == torch.float16:
+                    dx = dx.half()
+        return (dx, *grads_w)
+
+
+def tc_mlp(x, weights):
+    if x.shape[0] == 0:                      # no samples: keep the graph, nothing to launch
+        return x.new_zeros(0, weights[-1].shape[0], dtype=torch.float32) + 0.0 * sum(w.sum() for w in weights)
+    return TcMLPFunction.apply(x, *weights)

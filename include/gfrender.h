@@ -15,6 +15,7 @@
 #ifndef GFRENDER_H_
 #define GFRENDER_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -185,6 +186,30 @@ GF_API uint64_t gf_adnerf_mlp_workspace_bytes(const GfAdnerfMlp* m, uint32_t n_s
 GF_API int gf_adnerf_mlp_forward(const GfAdnerfMlp* m, const float* rays_o, const float* rays_d, const float* z_vals,
                                  const float* viewdirs, const float* cond, uint32_t R, uint32_t S, float* raw, void* workspace,
                                  uint64_t workspace_bytes, gf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Tensor-core linear layers of the TRAINING step.  Replace the library GEMMs behind the bias-free MLPs of the field
+ * (modules/radnerfs/cond_encoder.py:92-111: nn.Linear(bias=False) + ReLU; called from radnerf.py:73-105 under
+ * tasks/radnerfs/radnerf.py:185-216) in forward, data-gradient and weight-gradient form; fp16 operands, fp32 accumulation
+ * (= the reference's `amp: true` arithmetic).  Tensors travel as 128-row tiles of 64-column fp16 chunks
+ * ([tile][chunk][128 rows x 128 B, 16-byte units XOR-swizzled by row & 7]); gf_tl_tiles_bytes gives the size.
+ * ------------------------------------------------------------------------------------ */
+GF_API size_t gf_tl_tiles_bytes(uint32_t M, uint32_t chunks);
+/* rows [M][ld] (fp32, or fp16 if src_f16) columns [0, K) (x *scale if non-NULL, a device scalar) -> tiles of `chunks` chunks, zero padded */
+GF_API int gf_tl_pack(const void* src, int src_f16, uint32_t ld, uint32_t K, uint32_t M, uint32_t chunks, const float* scale, void* tiles,
+                      gf_stream_t stream);
+/* W [N][K] fp32 (nn.Linear.weight) -> fp16 image of `chunks` blocks [rows_pad x 128 B]; rows_pad % 16 == 0, >= N, <= 256 */
+GF_API int gf_tl_weight_image(const float* W, uint32_t N, uint32_t K, uint32_t rows_pad, uint32_t chunks, void* img, gf_stream_t stream);
+/* dgrad = 0: D = A W^T (F.linear forward; D has rows_pad columns); dgrad = 1: D = A W (grad_input; D has 64 * w_chunks columns).
+ * D (x ReLU mask of the saved activation tiles `mask` if non-NULL) (ReLU if relu) -> fp16 tiles `out` and / or fp32 rows
+ * out_f32 [M][ld_f32] columns [0, n_f32) x *out_scale. */
+GF_API int gf_tl_gemm(const void* a, uint32_t a_chunks, const void* w_img, uint32_t w_rows, uint32_t w_chunks, int dgrad, uint32_t M, void* out,
+                      uint32_t out_chunks, int relu, const void* mask, uint32_t mask_chunks, float* out_f32, uint32_t ld_f32, uint32_t n_f32,
+                      const float* out_scale, gf_stream_t stream);
+/* grad_weight: dw += *scale * P[:, 64 p_c0 : 64 p_c0 + 128]^T Q[:, 0:N] over the M samples (P, Q tiles); transposed = 0: dw[m * ld + n],
+ * 1: dw[n * ld + m]; entries m < rows_m, n < cols_n.  dw (fp32) is accumulated into with reductions: zero it first. */
+GF_API int gf_tl_wgrad(const void* p, uint32_t p_chunks, uint32_t p_c0, const void* q, uint32_t q_chunks, uint32_t N, uint32_t M, float* dw,
+                       uint32_t ld, uint32_t rows_m, uint32_t cols_n, int transposed, const float* scale, gf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Fused frame renderer: replaces the eval branch of NeRFRenderer.render()

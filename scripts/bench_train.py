@@ -21,18 +21,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--amp", action="store_true", help="fp16 autocast + GradScaler on both arms (the reference trains with amp: true)")
     ap.add_argument("--graph-only", action="store_true", help="(internal) only the CUDA-graph-captured step, in its own process")
+    ap.add_argument("--mlp", default="torch", choices=["torch", "tc"],
+                    help="MLP backend of OUR arm: library GEMMs under autograd, or the gf_tl_* tcgen05 operators (fp16 operands, fp32 accumulation = amp arithmetic)")
+    ap.add_argument("--no-ref", action="store_true", help="skip the reference's own step")
     args = ap.parse_args()
-    print(json.dumps(run(args.steps, args.warmup, 0, args.rays, args.amp, args.graph_only)), flush=True)
+    print(json.dumps(run(args.steps, args.warmup, 0, args.rays, args.amp, args.graph_only, args.mlp, args.no_ref)), flush=True)
 
 
-def run(steps=20, warmup=5, local=0, rays=4096, amp=False, graph_only=False):
-    args = argparse.Namespace(steps=steps, warmup=warmup, rays=rays, amp=amp)
+def run(steps=20, warmup=5, local=0, rays=4096, amp=False, graph_only=False, mlp="torch", no_ref=False):
+    args = argparse.Namespace(steps=steps, warmup=warmup, rays=rays, amp=amp, mlp=mlp)
     import torch
     from geneface_b200 import synthetic, utils
     assert torch.cuda.is_available(), "needs a GPU"
     dev = torch.device("cuda", local)
     H = W = 512
-    model, hp = synthetic.build_model(torso=False, bitfield='S', seed=0, device=dev)
+    model, hp = synthetic.build_model(torso=False, bitfield='S', seed=0, device=dev, train_mlp_backend=mlp)
     model.train()
     fi = synthetic.frame_inputs(H, W, device=dev)
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3)
@@ -83,16 +86,16 @@ def run(steps=20, warmup=5, local=0, rays=4096, amp=False, graph_only=False):
         torch.cuda.synchronize()
     rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:12]
     tot = sum(r.device_time_total for r in prof.key_averages()) or 1.0
-    ref_line = reference_train_step(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args)
+    ref_line = {"skipped": True} if no_ref else reference_train_step(model, hp, fi, rays_o, rays_d, bgc, bg_color, target, args)
     # the graph-captured step runs in its own process: a failed capture must not leave this process's RNG / context in capture mode
     import subprocess
     try:
-        cmd = [sys.executable, os.path.abspath(__file__), "--graph-only", "--rays", str(args.rays), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        cmd = [sys.executable, os.path.abspath(__file__), "--graph-only", "--rays", str(args.rays), "--steps", str(args.steps), "--warmup", str(args.warmup), "--mlp", mlp]
         r = subprocess.run(cmd + (["--amp"] if args.amp else []), capture_output=True, text=True, timeout=240)
         graph_ms = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else {"unavailable": (r.stderr or r.stdout)[-400:]}
     except Exception as e:  # noqa: BLE001
         graph_ms = {"unavailable": repr(e)[:300]}
-    line = {"metric": "train step, %d rays (march_rays_train + field + composite + backward + Adam)" % args.rays, "ms_per_step": ms, "amp": bool(args.amp),
+    line = {"metric": "train step, %d rays (march_rays_train + field + composite + backward + Adam)" % args.rays, "ms_per_step": ms, "amp": bool(args.amp), "mlp": mlp,
             "reference_cuda": ref_line, "mean_count": int(model.mean_count), "cuda_graph": graph_ms, "grid_backward": os.environ.get("GF_GRID_BWD", "b200 (privatised small levels)"),
             "rays_per_s": args.rays / (ms / 1000.0), "loss": float(loss), "grads_finite": bool(all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)),
             "top_kernels": [{"name": r.key[:70], "share": r.device_time_total / tot, "calls": r.count} for r in rows]}

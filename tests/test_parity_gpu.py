@@ -266,14 +266,20 @@ def test_grid_encoder(oracle_ops, D, gridtype, interp):
     assert_close((0.5 * out + o_b).cpu().numpy(), o_c.cpu().numpy(), rel=1e-4, abs_=1e-5, what="linearity")
 
 
-@pytest.mark.parametrize("mode", ["priv", "plain"])
+@pytest.mark.parametrize("mode", ["priv", "plain", "priv-clustered"])
 @pytest.mark.parametrize("D", [2, 3])
 def test_grid_backward_kernels_and_fp16_path(oracle_ops, D, mode):
     """Hash-grid backward in both kernel forms -- `priv`: shared-memory privatised small levels + vector
     reductions (forced here; by default chosen for batches >= 131,072 samples), `plain`: one vector reduction per corner (+ the warp-uniform aggregation) -- against the
     oracle's fp64 re-accumulation of the same scatter, on a LARGE batch (the regime privatisation is for), in fp32 and through the
     fp16 path (dtype = 1: half gradients, half2 reductions, as the reference runs under autocast, grid.py:43-44,65-89).
+    `priv` also switches on the shared-memory update cache of the larger 2-D levels (default: batches >= 65,536 samples); `priv-clustered` runs it
+    on coordinates concentrated in a few cells (what the ambient network's outputs look like), the case it exists for.
     The mode is latched at first use per process, so each runs in a child process."""
+    clustered = mode.endswith("-clustered")
+    mode = mode.split("-")[0]
+    if clustered and D != 2:
+        pytest.skip("the update cache serves the 2-D grids (network-output coordinates)")
     import os
     import subprocess
     import sys
@@ -289,6 +295,8 @@ D = {D}
 offsets, S, emb = scenes.grid_setup(D, seed=20 + D)
 B, L, C = 200000, 16, 2
 x = scenes.unit_points(B, D, seed=30 + D)
+if {clustered}:
+    x = (0.37 + 0.002 * np.random.RandomState(31).randn(B, D)).astype(np.float32)
 grad = (np.random.RandomState(40).randn(L, B, C) * 0.1).astype(np.float32)
 gg_ref, _ = cpu_ops.grid_encode_backward(grad, x, emb, offsets, S, 16, None, 1, False, 0)
 cu = lambda a, dt=None: (torch.from_numpy(np.ascontiguousarray(a)).cuda() if dt is None else torch.from_numpy(np.ascontiguousarray(a)).cuda().to(dt))
