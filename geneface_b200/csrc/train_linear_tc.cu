@@ -216,10 +216,19 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tl_gemm(const TlGemmArgs a) {
                         *reinterpret_cast<uint4*>(dst + sw128(row, (g & 1) * 4 + u)) = make_uint4(p[4 * u], p[4 * u + 1], p[4 * u + 2], p[4 * u + 3]);
                 }
                 if (a.out_f32 && i < a.M) {
+                    // a thread owns one row: 16-byte stores when the row pitch allows it (n_f32 is then a multiple of 4 -- the host pads the pitch of
+                    // odd-width outputs).  Scalar stores made the row-major outputs (32 lanes x 4 B, each in another row) the slowest launches of a step.
                     float* dst = a.out_f32 + i * a.ld_f32;
-                    #pragma unroll
-                    for (int e = 0; e < 32; e++)
-                        if (32 * g + e < a.n_f32) dst[32 * g + e] = v[e] * oscale;
+                    if ((a.ld_f32 & 3) == 0 && (a.n_f32 & 3) == 0) {
+                        #pragma unroll
+                        for (int e = 0; e < 32; e += 4)
+                            if (32 * g + e < a.n_f32)
+                                *reinterpret_cast<float4*>(dst + 32 * g + e) = make_float4(v[e] * oscale, v[e + 1] * oscale, v[e + 2] * oscale, v[e + 3] * oscale);
+                    } else {
+                        #pragma unroll
+                        for (int e = 0; e < 32; e++)
+                            if (32 * g + e < a.n_f32) dst[32 * g + e] = v[e] * oscale;
+                    }
                 }
             }
             // out tiles wider than the accumulator (N = 16 / 144 rounded up to whole chunks): zero the rest so that later products read defined values

@@ -67,13 +67,16 @@ class TcMLPFunction(torch.autograd.Function):
         assert supported(dims), "TcMLPFunction: layer widths outside the tensor-core envelope"
         acts = [_pack(x, K0, _chunks(K0))]                     # tile-major fp16 inputs of every layer (saved for backward)
         imgs = []
-        y = torch.empty(M, dims[-1], dtype=torch.float32, device=x.device)
+        # fp32 rows leave the kernels with 16-byte stores: the pitch of an odd-width output is padded to a multiple of 4 (the caller sees a view)
+        n_out, ld_y = dims[-1], (dims[-1] + 3) // 4 * 4
+        y_full = torch.empty(M, ld_y, dtype=torch.float32, device=x.device)
+        y = y_full[:, :n_out]
         for l, w in enumerate(ws):
             img, rows, chunks = _image(w)
             imgs.append((img, rows, chunks))
             last = l == len(ws) - 1
             if last:
-                check(L.gf_tl_gemm(ptr(acts[l]), chunks, ptr(img), rows, chunks, 0, M, None, 0, 0, None, 0, ptr(y), y.stride(0), dims[-1], None, stream_ptr()),
+                check(L.gf_tl_gemm(ptr(acts[l]), chunks, ptr(img), rows, chunks, 0, M, None, 0, 0, None, 0, ptr(y_full), ld_y, min(ld_y, rows), None, stream_ptr()),
                       "gf_tl_gemm(forward, output layer)")
             else:
                 h = _tiles(M, 2, x.device)
@@ -119,8 +122,11 @@ class TcMLPFunction(torch.autograd.Function):
                 check(L.gf_tl_gemm(ptr(g), g_chunks, ptr(img), rows, chunks, 1, M, ptr(gn), 2, 0, ptr(acts[l]), 2, None, 0, 0, None, stream_ptr()), "gf_tl_gemm(dgrad)")
                 g, g_chunks = gn, 2
             elif ctx.needs_input_grad[0]:
-                dx = torch.empty(M, K_l, dtype=torch.float32, device=dev)
-                check(L.gf_tl_gemm(ptr(g), g_chunks, ptr(img), rows, chunks, 1, M, None, 0, 0, None, 0, ptr(dx), K_l, K_l, ptr(inv), stream_ptr()), "gf_tl_gemm(grad_input)")
+                ld_x = (K_l + 3) // 4 * 4
+                dx_full = torch.empty(M, ld_x, dtype=torch.float32, device=dev)
+                check(L.gf_tl_gemm(ptr(g), g_chunks, ptr(img), rows, chunks, 1, M, None, 0, 0, None, 0, ptr(dx_full), ld_x, min(ld_x, 64 * chunks), ptr(inv), stream_ptr()),
+                      "gf_tl_gemm(grad_input)")
+                dx = dx_full[:, :K_l]
                 if ctx.x_grad == torch.float16:
                     dx = dx.half()
         return (dx, *grads_w)
