@@ -197,6 +197,29 @@ __device__ __forceinline__ uint32_t sp_setup(uint8_t* smem, uint32_t sbase, cons
 // z+1 plane only when it exists.  Interpolation is bilinear per z-plane, then a lerp in z (the fp32 result differs from the
 // reference's corner-order sum by rounding only; it is rounded to fp16 right after).
 // ALLFLAT: every level of the batch drops z and is not hashed -> only the 4 corners of the z0 plane exist (uniform fast path).
+// floor() of a grid coordinate without the conversion pipe.  p = x * scale + 0.5 lies in [0.5, 2^23): adding 2^23 with round-toward-minus-infinity
+// leaves floor(p) in the mantissa, exactly; the integer is the low 23 bits and the float is recovered by an exact subtraction.  Replaces F2I.FLOOR +
+// I2F (two conversion-pipe instructions, ~4x the issue cost and ~3x the latency of an FADD, in front of every level's dependent address chain) by
+// FADD.RM + LOP + FADD.  Bit-identical to floorf / (float) for this range.  -DGF_FAST_FLOOR=0 restores the conversions (A/B).
+// experiment switch: compile the smoothstep interpolation out (linear-interpolation models only; measurement aid)
+#ifndef GF_ASSUME_LINEAR
+#define GF_ASSUME_LINEAR 0
+#endif
+#ifndef GF_FAST_FLOOR
+#define GF_FAST_FLOOR 1
+#endif
+__device__ __forceinline__ uint32_t floor_split(float& p) {
+#if GF_FAST_FLOOR
+    const float t = __fadd_rd(p, 8388608.0f);
+    p = __fsub_rn(p, __fsub_rn(t, 8388608.0f));
+    return __float_as_uint(t) & 0x7fffffu;
+#else
+    const uint32_t g = (uint32_t)floorf(p);
+    p = __fsub_rn(p, (float)g);
+    return g;
+#endif
+}
+
 template <bool ALLFLAT>
 __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x, float y, float z, float2 (&out)[4]) {
     float fx[4], fy[4], fz[4];
@@ -206,9 +229,8 @@ __device__ __forceinline__ void gather3_dyn4(const GridDesc& g, int l0, float x,
         const int l = l0 + i;
         const float scale = g.lv.scale[l];
         float px = __fmaf_rn(x, scale, 0.5f), py = __fmaf_rn(y, scale, 0.5f), pz = __fmaf_rn(z, scale, 0.5f);
-        const uint32_t gx = (uint32_t)floorf(px), gy = (uint32_t)floorf(py), gz = (uint32_t)floorf(pz);
-        px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy); pz = __fsub_rn(pz, (float)gz);
-        if (g.interp == 1) { px = smooth_(px); py = smooth_(py); pz = smooth_(pz); }
+        const uint32_t gx = floor_split(px), gy = floor_split(py), gz = floor_split(pz);
+        if (!GF_ASSUME_LINEAR && g.interp == 1) { px = smooth_(px); py = smooth_(py); pz = smooth_(pz); }
         fx[i] = px; fy[i] = py; fz[i] = pz;
         const float2* __restrict__ tab = g.lbase[l];
         const uint32_t mask = g.lv.mask[l], sy = g.lv.sy[l], sz = g.lv.sz[l];
@@ -261,9 +283,8 @@ __device__ __forceinline__ void gather2_dyn8(const GridDesc& g, int l0, float x,
         const int l = l0 + i;
         const float scale = g.lv.scale[l];
         float px = __fmaf_rn(x, scale, 0.5f), py = __fmaf_rn(y, scale, 0.5f);
-        const uint32_t gx = (uint32_t)floorf(px), gy = (uint32_t)floorf(py);
-        px = __fsub_rn(px, (float)gx); py = __fsub_rn(py, (float)gy);
-        if (g.interp == 1) { px = smooth_(px); py = smooth_(py); }
+        const uint32_t gx = floor_split(px), gy = floor_split(py);
+        if (!GF_ASSUME_LINEAR && g.interp == 1) { px = smooth_(px); py = smooth_(py); }
         fx[i] = px; fy[i] = py;
         const float2* __restrict__ tab = g.lbase[l];
         const uint32_t mask = g.lv.mask[l], sy = g.lv.sy[l];

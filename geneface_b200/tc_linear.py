@@ -6,8 +6,9 @@ Arithmetic: fp16 operands, fp32 accumulation, fp32 weights and gradients -- what
 default `amp: true`; the incoming gradient is scaled by a power of two chosen on the device (largest |dy| -> ~2^8) before it is rounded to
 fp16 and the factor is divided out of grad_input / grad_weight in their fp32 epilogues, so the result does not depend on an outer GradScaler.
 
-Envelope: hidden width 128 (the tensor-core tile height of the weight-gradient product), 2 or more layers, input / output widths <= 256 / 144.
-`supported(mlp)` says whether an `MLP` module is inside it; outside it `MLP.forward` keeps the library path.
+Envelope: hidden width <= 128 (narrower hidden layers -- the 64 / 32-wide torso nets -- run zero-padded to the 128-row tensor-core tile of the
+weight-gradient product), 2 or more layers, input / output widths <= 256 / 144.  `supported(dims)` says whether an `MLP` is inside it; outside it
+`MLP.forward` keeps the library path.
 """
 import torch
 
@@ -27,7 +28,7 @@ def supported(dims):
     """dims = [in, hidden, ..., hidden, out]"""
     if len(dims) < 3:
         return False
-    return all(h == 128 for h in dims[1:-1]) and dims[0] <= 256 and dims[-1] <= 144
+    return all(16 <= h <= 128 for h in dims[1:-1]) and dims[0] <= 256 and dims[-1] <= 144
 
 
 def _tiles(M, chunks, device):
@@ -41,9 +42,10 @@ def _pack(src, K, chunks, scale=None):
     return out
 
 
-def _image(W):
+def _image(W, rows=None, chunks=None):
+    """fp16 image of W [N, K]: `chunks` blocks of [rows x 128 B]; defaults: rows = ceil16(N), chunks = ceil(K / 64) (zero padded)"""
     N, K = W.shape
-    rows, chunks = _pad16(N), _chunks(K)
+    rows, chunks = rows or _pad16(N), chunks or _chunks(K)
     img = torch.empty(rows * chunks * 128, dtype=torch.uint8, device=W.device)
     check(_lib.lib().gf_tl_weight_image(ptr(W), N, K, rows, chunks, ptr(img), stream_ptr()), "gf_tl_weight_image")
     return img, rows, chunks
@@ -72,9 +74,11 @@ class TcMLPFunction(torch.autograd.Function):
         y_full = torch.empty(M, ld_y, dtype=torch.float32, device=x.device)
         y = y_full[:, :n_out]
         for l, w in enumerate(ws):
-            img, rows, chunks = _image(w)
-            imgs.append((img, rows, chunks))
             last = l == len(ws) - 1
+            # hidden layers are held 128 wide (2 chunks): a narrower layer's extra rows / columns are zero in the images, so its padded activations and
+            # gradients are exactly zero
+            img, rows, chunks = _image(w, rows=None if last else 128, chunks=None if l == 0 else 2)
+            imgs.append((img, rows, chunks))
             if last:
                 check(L.gf_tl_gemm(ptr(acts[l]), chunks, ptr(img), rows, chunks, 0, M, None, 0, 0, None, 0, ptr(y_full), ld_y, min(ld_y, rows), None, stream_ptr()),
                       "gf_tl_gemm(forward, output layer)")

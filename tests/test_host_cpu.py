@@ -310,3 +310,32 @@ def test_render_sequence_checkpoint_unwrap_and_background_options():
     ds_bg = np.full((4, 6, 3), 0.25, np.float32)
     assert rs.background_image("", ds_bg, 4, 6) is not None and np.array_equal(rs.background_image("", ds_bg, 4, 6), ds_bg)
     assert rs.background_image("white", ds_bg, 4, 6).min() == 1.0 and rs.background_image("black", ds_bg, 4, 6).max() == 0.0
+
+
+def test_training_mlp_backend_selection_and_envelope():
+    """hparams['train_mlp_backend'] reaches the three field MLPs; the tensor-core envelope covers exactly the head field's nets (cond_encoder.py:92-111 /
+    radnerf.py:73-105 shapes) and not the 64/32-wide torso nets; on the CPU (no grad-capable CUDA input) MLP.forward stays on the library path and
+    equals the plain Linear/ReLU stack; the tensor-core function itself refuses to run without a GPU."""
+    import torch
+    from geneface_b200 import synthetic, tc_linear
+    from geneface_b200.renderer import RADNeRF, RADNeRFTorso
+    m = RADNeRF(synthetic.may_hparams(train_mlp_backend='tc'))
+    nets = (m.ambient_net, m.sigma_net, m.color_net)
+    assert [n.backend for n in nets] == ['tc'] * 3
+    assert [n._dims() for n in nets] == [[96, 128, 128, 2], [64, 128, 128, 129], [148, 128, 3]]
+    assert all(tc_linear.supported(n._dims()) for n in nets)
+    assert RADNeRF(synthetic.may_hparams()).sigma_net.backend == 'torch'
+    t = RADNeRFTorso(synthetic.may_hparams(train_mlp_backend='tc'))
+    assert not tc_linear.supported(t.torso_deform_net._dims()) and not tc_linear.supported(t.torso_canonicial_net._dims())
+    assert not tc_linear.supported([96, 128]) and not tc_linear.supported([300, 128, 3]) and not tc_linear.supported([64, 128, 200])
+    x = torch.randn(10, 96, requires_grad=True)
+    y = m.ambient_net(x)                                  # CPU tensor: library path even with backend = 'tc'
+    h = x
+    for l, layer in enumerate(m.ambient_net.net):
+        h = layer(h)
+        if l != 2:
+            h = torch.relu(h)
+    assert torch.equal(y, h)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            tc_linear.tc_mlp(x, [layer.weight for layer in m.ambient_net.net])
