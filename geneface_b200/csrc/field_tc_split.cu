@@ -28,10 +28,12 @@
 namespace gf {
 
 constexpr int SP_THREADS = 512;        // kernel B: warps 0-7 producers, 8-11 consumer stream 0, 12-15 consumer stream 1
-// kernel A: GF_A_PROD_WG producer warpgroups, default 2 (same warp roles as kernel B).  3 (warps 0-11 producers, 12-15 stream 0, 16-19 stream 1, 96
-// registers per thread) was measured SLOWER: 10.09 vs 8.75 ms per frame.  With a third gathering warpgroup every producer and both consumer streams slow
-// down in proportion (the same 4-level batch takes 3,300 instead of 2,450 cycles, the split epilogue 2,700 instead of 2,050): the SM's issue slots, not
-// the number of gathering warps, bound this kernel (profiles/r02_summary.md section 7).
+// kernel A: GF_A_PROD_WG producer warpgroups, default 2 (same warp roles as kernel B).  3 (warps 0-11 producers, 12-15 stream 0, 16-19 stream 1) was
+// measured SLOWER twice: with 96 registers for every thread 10.09 vs 8.75 ms per frame (the same 4-level batch takes 3,300 instead of 2,450 cycles, the
+// split epilogue 2,700 instead of 2,050), and with setmaxnreg (producers 112, consumers 72 registers, non-pipelined consumer epilogues) 8.72 / 8.98 vs
+// 8.57 / 8.66 ms.  More gathering warps do not help: the SM's issue slots bound this kernel (profiles/r02_summary.md section 7).  Note for setmaxnreg:
+// the increase is served from the registers the CTA itself released (USETMAXREG.TRY_ALLOC.CTAPOOL) -- the launch-time slack does not count, so
+// consumers 80 / producers 112 (256 x 16 < 384 x 16) spins forever.
 #ifndef GF_A_PROD_WG
 #define GF_A_PROD_WG 2
 #endif
@@ -329,6 +331,11 @@ __global__ void __launch_bounds__(SPA_THREADS, 1) k_tc_amb(const SpArgs a) {
 
     if (warp < 4 * SPA_PROD_WG) {
         // ------------------------------------------------ producers ------------------------------------------------
+#if GF_A_PROD_WG == 3
+        // 640 threads start with 96 registers each; the gathering warpgroups take 112 (32 loads in flight need them), the consumer warpgroups give
+        // theirs back (72: non-pipelined epilogues).  The increase is served from the registers the CTA itself released (CTAPOOL): 256 x 24 = 384 x 16
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+#endif
         const uint32_t half = tid >> 7, row = tid & 127;     // half = producer warpgroup 0 .. SPA_PROD_WG-1
         uint32_t flat_units = 0;          // bit u: levels 4u..4u+3 all drop z and are not hashed
         #pragma unroll
@@ -422,6 +429,9 @@ __global__ void __launch_bounds__(SPA_THREADS, 1) k_tc_amb(const SpArgs a) {
         // warp-uniform copies of the warp index and the TMEM base: the tcgen05.mma operands derived from them then live in uniform registers.
         // Derived from threadIdx / a shared-memory load they were per-thread values, and every MMA was issued through an ELECT / R2UR
         // broadcast loop of 13 instructions (~75 cycles per MMA on the stream's critical path, longer than the MMA itself).
+#if GF_A_PROD_WG == 3
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+#endif
         const uint32_t warp_u = __shfl_sync(0xffffffffu, warp, 0), tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t stream = (warp_u - 4 * SPA_PROD_WG) >> 2, row = tid & 127;
         const uint32_t t_d = tmem_u + (((warp_u & 3) * 32) << 16) + stream * SP_TM_STREAM;
@@ -459,7 +469,11 @@ __global__ void __launch_bounds__(SPA_THREADS, 1) k_tc_amb(const SpArgs a) {
             tc_fence_after();
             TT_LSTAMP(0, stream, j, 2);
             if (lead_warp && elect_one_sync()) mbar_arrive(bar_empty + 8 * slot);                // the feature tile has been consumed
+#if GF_A_PROD_WG == 3
+            epilogue_relu_to_A_n<true, 4>(t_d, t_d + SP_TM_AHI, t_d + SP_TM_ALO, 0, bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);      // 80-register budget
+#else
             epilogue_split_to_A_pipe(t_d, t_d + SP_TM_AHI, t_d + SP_TM_ALO, bias_cond, dbg ? dbg + 0 * 128 * 144 : nullptr);
+#endif
             TT_LSTAMP(0, stream, j, 3);
             tc_fence_before();
             bar_named(1 + stream, 128);
@@ -485,6 +499,20 @@ __global__ void __launch_bounds__(SPA_THREADS, 1) k_tc_amb(const SpArgs a) {
             // constant path's throughput made this phase 2,400 cycles per tile (the longest of the stream's chain; tc_timeline).  The accumulator
             // load of the next 32 columns is in flight while the current ones are reduced.
             float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;          // (even, odd) column partial sums of the two outputs
+#if GF_A_PROD_WG == 3
+            #pragma unroll 1
+            for (int c = 0; c < 4; c++) {                                // 80-register budget: one 32-column load at a time
+                float v[32];
+                tmem_ld32(t_d + 32 * c, v);
+                #pragma unroll
+                for (int q = 0; q < 32; q += 2) {
+                    const float4 w = lds128(sbase + L::W2 + 16 * (16 * c + (q >> 1)));
+                    const float2 h = make_float2(fmaxf(v[q], 0.f), fmaxf(v[q + 1], 0.f));
+                    acc0 = ffma2(h, make_float2(w.x, w.y), acc0);
+                    acc1 = ffma2(h, make_float2(w.z, w.w), acc1);
+                }
+            }
+#else
             {
                 uint32_t r[2][32];
                 tmem_ld32_issue(t_d, r[0]);
@@ -507,6 +535,7 @@ __global__ void __launch_bounds__(SPA_THREADS, 1) k_tc_amb(const SpArgs a) {
                     if (c < 3) tmem_wait_ld32(r[(c + 1) & 1]);
                 }
             }
+#endif
             const float s0 = acc0.x + acc0.y, s1 = acc1.x + acc1.y;
             if (dbg) { dbg[2 * 128 * 144 + 0] = s0; dbg[2 * 128 * 144 + 1] = s1; }
             if (i < M) a.io.amb_pos[i] = make_float2(tanhf(s0), tanhf(s1));
