@@ -96,11 +96,12 @@ def test_tc_mlp_exact_on_small_integers():
 
 def test_train_step_with_tc_backend_matches_the_library_backend():
     """one training step of the head model (march_rays_train + field + composite + backward) with hparams['train_mlp_backend'] = 'tc' against the
-    same step on library GEMMs: loss and every parameter gradient agree to fp16-operand accuracy"""
+    same step on library GEMMs in fp32, with the library path under fp16 autocast (the reference's `amp: true`, loss scaled as its GradScaler does) as
+    the yardstick: the tensor-core backend must be as close to the fp32 gradients as autocast is."""
     from geneface_b200 import synthetic, utils
     H = W = 64
     grads = {}
-    for backend in ("torch", "tc"):
+    for name, backend, amp in (("fp32", "torch", False), ("autocast", "torch", True), ("tc", "tc", False)):
         model, hp = synthetic.build_model(torso=False, bitfield='S', seed=0, train_mlp_backend=backend)
         model.train()
         fi = synthetic.frame_inputs(H, W)
@@ -111,26 +112,27 @@ def test_train_step_with_tc_backend_matches_the_library_backend():
         bgc = utils.get_bg_coords(H, W, "cuda")[:, inds]
         target = torch.rand(1, 1024, 3, device="cuda", generator=g)
         torch.manual_seed(4)
-        out = model.render(rays_o, rays_d, fi['cond'], bgc, fi['poses6'], index=0, dt_gamma=hp['dt_gamma'], bg_color=fi['bg_color'][:, inds], perturb=True,
-                           force_all_rays=False, max_steps=hp['max_steps'])
-        loss = ((out['rgb_map'].float() - target) ** 2).mean()
-        loss.backward()
-        grads[backend] = (loss.item(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
-    (l0, g0), (l1, g1) = grads["torch"], grads["tc"]
+        with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+            out = model.render(rays_o, rays_d, fi['cond'], bgc, fi['poses6'], index=0, dt_gamma=hp['dt_gamma'], bg_color=fi['bg_color'][:, inds], perturb=True,
+                               force_all_rays=False, max_steps=hp['max_steps'])
+            loss = ((out['rgb_map'].float() - target) ** 2).mean()
+        ls = 1024.0 if amp else 1.0
+        (loss * ls).backward()
+        grads[name] = (loss.item(), {n: p.grad.detach().double() / ls for n, p in model.named_parameters() if p.grad is not None})
+    (l0, g0), (la, ga), (l1, g1) = grads["fp32"], grads["autocast"], grads["tc"]
     assert abs(l0 - l1) <= 2e-3 * abs(l0), (l0, l1)
     assert g0.keys() == g1.keys()
-    worst = 0.0
-    # tensors whose gradient vanishes analytically (e.g. the scalar bias in front of the attention softmax: shift invariance) hold rounding noise only:
-    # errors are measured against max(|reference|, 1e-4 of the largest gradient norm of the step)
-    floor = 1e-4 * max(g.double().norm().item() for g in g0.values())
+    # tensors whose gradient vanishes analytically hold rounding noise only: errors are measured against max(|reference|, 1e-4 of the largest gradient norm)
+    floor = 1e-4 * max(g.norm().item() for g in g0.values())
+    worst, worst_a = 0.0, 0.0
     for n in g0:
-        ref = g0[n].double()
-        err = ((g1[n].double() - ref).norm() / max(ref.norm().item(), floor)).item()       # relative Frobenius error (a ReLU mask flipped by fp16 rounding moves single entries)
-        worst = max(worst, err)
-        # the chain loss -> colour net -> sigma net -> 2-D grid -> ambient net -> condition encoder compounds the ~2 % per-MLP deviation every fp16 forward
-        # has (measured above against autocast); its far end (the condition encoder's first layer) was 9.4e-2 / cosine 0.9974 on the B200
-        assert err < (0.15 if ref.numel() >= 16 else 0.35), f"{n}: relative error {err:.2e}"     # scalars / tiny tensors: no averaging (a scalar conv bias was 2.2e-1)
-        if ref.numel() > 1 and ref.norm().item() > floor:
-            cos = (torch.dot(g1[n].double().flatten(), ref.flatten()) / (g1[n].double().norm() * ref.norm())).item()
-            assert cos > 0.98, f"{n}: cosine {cos:.5f}"            # measured 0.9897 (position grid) .. 1.0
-    print("tc backend vs library backend: loss %.6f / %.6f, worst relative gradient deviation (Frobenius) %.2e" % (l0, l1, worst))
+        ref = g0[n]
+        den = max(ref.norm().item(), floor)
+        err, err_a = (g1[n] - ref).norm().item() / den, (ga[n] - ref).norm().item() / den       # relative Frobenius errors
+        worst, worst_a = max(worst, err), max(worst_a, err_a)
+        # as close to fp32 as the reference's own amp arithmetic is (+ head-room for run-to-run differences: the grid gradients are reductions in
+        # arbitrary order), and never far off in absolute terms
+        assert err < max(2.0 * err_a, 0.05), f"{n}: {err:.2e} of its norm (library path under autocast: {err_a:.2e})"
+        assert err < 0.4, f"{n}: {err:.2e}"
+    print("whole-step gradients vs fp32: tensor-core backend worst %.2e, library path under autocast worst %.2e (relative Frobenius); loss %.6f / %.6f / %.6f"
+          % (worst, worst_a, l0, la, l1))
