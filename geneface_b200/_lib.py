@@ -126,7 +126,7 @@ _SIGS = {
     "gf_adnerf_mlp_workspace_bytes": [c_vp, c_u32],
     "gf_adnerf_mlp_forward": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_vp, c_vp, c_u64, c_vp],
     "gf_tl_tiles_bytes": [c_u32, c_u32],
-    "gf_tl_pack": [c_vp, c_int, c_u32, c_u32, c_u32, c_u32, c_vp, c_vp, c_vp],
+    "gf_tl_pack": [c_vp, c_int, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, c_vp, c_vp, c_vp],
     "gf_tl_weight_image": [c_vp, c_u32, c_u32, c_u32, c_u32, c_vp, c_vp],
     "gf_tl_gemm": [c_vp, c_u32, c_vp, c_u32, c_u32, c_int, c_u32, c_vp, c_u32, c_int, c_vp, c_u32, c_vp, c_u32, c_u32, c_vp, c_vp],
     "gf_tl_wgrad": [c_vp, c_u32, c_u32, c_vp, c_u32, c_u32, c_u32, c_vp, c_u32, c_u32, c_u32, c_int, c_vp, c_vp],

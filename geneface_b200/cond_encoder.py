@@ -67,10 +67,16 @@ class MLP(nn.Module):
         return [self.dim_in] + [self.dim_hidden] * (self.num_layers - 1) + [self.dim_out]
 
     def forward(self, x):
-        if self.backend == 'tc' and x.is_cuda and torch.is_grad_enabled() and x.dim() == 2:
+        """x: [M, dim_in], or a list of tensors standing for torch.cat(x, dim=1) (the tensor-core backend packs the parts without materialising the
+        concatenation; an expand()-ed row stays a broadcast)"""
+        parts = list(x) if isinstance(x, (list, tuple)) else None
+        x0 = parts[0] if parts else x
+        if self.backend == 'tc' and x0.is_cuda and torch.is_grad_enabled() and x0.dim() == 2:
             from . import tc_linear
             if tc_linear.supported(self._dims()):
-                return tc_linear.tc_mlp(x, [layer.weight for layer in self.net])
+                return tc_linear.tc_mlp(parts if parts else x, [layer.weight for layer in self.net])
+        if parts:
+            x = torch.cat(parts, dim=1)
         for l, layer in enumerate(self.net):
             x = layer(x)
             if l != self.num_layers - 1:

@@ -44,18 +44,20 @@ __host__ __device__ constexpr uint32_t idesc_f16_t(uint32_t N, uint32_t a_mn, ui
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------- pack
-// rows -> tiles.  One thread per (row, 16-byte unit).  src_f16: source is __half; scale: optional device scalar multiplied in.
-__global__ void k_tl_pack(const void* __restrict__ src, int src_f16, uint32_t ld, uint32_t K, uint32_t M, uint32_t chunks, const float* __restrict__ scale,
-                          uint8_t* __restrict__ tiles) {
+// rows -> tiles.  One thread per (row, 16-byte unit) of the column range [col0, col1) of the tiles (col0, col1 multiples of 8): columns
+// col0 .. col0 + K - 1 come from src[r * ld + (col - col0)] (ld = 0: one row broadcast to every sample), the rest of the range is zero.  Several calls
+// with adjacent ranges assemble a concatenated input without materialising it.  src_f16: source is __half; scale: optional device scalar.
+__global__ void k_tl_pack(const void* __restrict__ src, int src_f16, uint32_t ld, uint32_t K, uint32_t M, uint32_t chunks, uint32_t col0, uint32_t col1,
+                          const float* __restrict__ scale, uint8_t* __restrict__ tiles) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t ntiles = (M + 127) / 128, units = chunks * 8;
+    const uint32_t ntiles = (M + 127) / 128, units = (col1 - col0) >> 3;
     if (t >= ntiles * 128 * units) return;
-    const uint32_t r = t / units, u = t % units, tile = r >> 7, row = r & 127, c = u >> 3, uu = u & 7;
+    const uint32_t r = t / units, u = (col0 >> 3) + t % units, tile = r >> 7, row = r & 127, c = u >> 3, uu = u & 7;
     const float s = scale ? *scale : 1.0f;
     __align__(16) __half h[8];
     #pragma unroll
     for (int e = 0; e < 8; e++) {
-        const uint32_t col = c * 64 + uu * 8 + e;
+        const uint32_t col = u * 8 + e - col0;
         float v = 0.f;
         if (r < M && col < K) v = src_f16 ? __half2float(reinterpret_cast<const __half*>(src)[(size_t)r * ld + col]) : reinterpret_cast<const float*>(src)[(size_t)r * ld + col];
         h[e] = __float2half_rn(v * s);
@@ -352,13 +354,16 @@ extern "C" {
 // bytes of one tensor in tile layout: ceil(M / 128) tiles x chunks x 16 KB
 GF_API size_t gf_tl_tiles_bytes(uint32_t M, uint32_t chunks) { return (size_t)((M + 127) / 128) * chunks * TL_CHUNK; }
 
-// rows [M][ld] (fp32, or fp16 if src_f16) columns [0, K) -> fp16 tiles of `chunks` 64-column chunks (zero padded); optional device scale
-GF_API int gf_tl_pack(const void* src, int src_f16, uint32_t ld, uint32_t K, uint32_t M, uint32_t chunks, const float* scale, void* tiles, gf_stream_t stream) {
+// rows [M][ld] (fp32, or fp16 if src_f16; ld = 0 broadcasts one row) columns [0, K) -> columns [col0, col0 + K) of fp16 tiles with `chunks` 64-column
+// chunks; the rest of [col0, col1) is zero filled (col1 = 0: up to the tile width).  col0, col1 multiples of 8.  Optional device scale.
+GF_API int gf_tl_pack(const void* src, int src_f16, uint32_t ld, uint32_t K, uint32_t M, uint32_t chunks, uint32_t col0, uint32_t col1, const float* scale,
+                      void* tiles, gf_stream_t stream) {
     GF_REQUIRE(src && tiles, "tl_pack: null pointer");
-    GF_REQUIRE(chunks >= 1 && K <= 64 * chunks, "tl_pack: K does not fit the chunks");
-    if (!M) return GF_OK;
-    const size_t total = (size_t)((M + 127) / 128) * 128 * chunks * 8;
-    k_tl_pack<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, src_f16, ld, K, M, chunks, scale, (uint8_t*)tiles);
+    if (!col1) col1 = 64 * chunks;
+    GF_REQUIRE(chunks >= 1 && (col0 & 7) == 0 && (col1 & 7) == 0 && col0 + K <= col1 && col1 <= 64 * chunks, "tl_pack: bad column range");
+    if (!M || col1 == col0) return GF_OK;
+    const size_t total = (size_t)((M + 127) / 128) * 128 * ((col1 - col0) >> 3);
+    k_tl_pack<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, src_f16, ld, K, M, chunks, col0, col1, scale, (uint8_t*)tiles);
     return check_launch("tl_pack");
 }
 

@@ -477,20 +477,22 @@ class RADNeRF(NeRFRenderer):
         return cond_feat
 
     def _trunk(self, position, cond_feat):
-        cond_feat = cond_feat.view(1, -1).repeat(position.shape[0], 1)
+        # the MLPs take the pieces of their concatenated inputs (radnerf.py:79,90,99 build them with repeat + cat); the library backend concatenates,
+        # the tensor-core backend packs the pieces straight into its tile layout and keeps the per-frame rows as broadcasts
+        cond_feat = cond_feat.view(1, -1).expand(position.shape[0], -1)
         pos_feat = self.position_embedder(position, bound=self.bound)
-        ambient_logit = self.ambient_net(torch.cat([pos_feat, cond_feat], dim=1)).float()
+        ambient_logit = self.ambient_net([pos_feat, cond_feat]).float()
         ambient_pos = torch.tanh(ambient_logit)
         ambient_feat = self.ambient_embedder(ambient_pos, bound=1)
-        h = self.sigma_net(torch.cat([pos_feat, ambient_feat], dim=-1))
+        h = self.sigma_net([pos_feat, ambient_feat])
         return trunc_exp(h[..., 0]), h[..., 1:], ambient_pos
 
     def forward(self, position, direction, cond_feat, individual_code):
         sigma, geo_feat, ambient_pos = self._trunk(position, cond_feat)
         parts = [self.direction_embedder(direction), geo_feat]
         if individual_code is not None:
-            parts.append(individual_code.view(1, -1).repeat(position.shape[0], 1))
-        color = torch.sigmoid(self.color_net(torch.cat(parts, dim=-1)))
+            parts.append(individual_code.view(1, -1).expand(position.shape[0], -1))
+        color = torch.sigmoid(self.color_net(parts))
         return sigma, color, ambient_pos
 
     def density(self, position, cond_feat, e=None):

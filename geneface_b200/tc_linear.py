@@ -38,7 +38,31 @@ def _tiles(M, chunks, device):
 def _pack(src, K, chunks, scale=None):
     M = src.shape[0]
     out = _tiles(M, chunks, src.device)
-    check(_lib.lib().gf_tl_pack(ptr(src), 1 if src.dtype == torch.float16 else 0, src.stride(0), K, M, chunks, ptr(scale), ptr(out), stream_ptr()), "gf_tl_pack")
+    check(_lib.lib().gf_tl_pack(ptr(src), 1 if src.dtype == torch.float16 else 0, src.stride(0), K, M, chunks, 0, 0, ptr(scale), ptr(out), stream_ptr()), "gf_tl_pack")
+    return out
+
+
+def _prep(x):
+    """a part of the input as the pack kernel reads it: fp32 / fp16, unit column stride; an expanded row (stride(0) == 0) stays a broadcast"""
+    x = x.detach()
+    if x.dtype not in (torch.float32, torch.float16):
+        x = x.float()
+    if x.dim() != 2 or (x.shape[1] > 1 and x.stride(1) != 1):
+        x = x.contiguous()
+    return x
+
+
+def _pack_parts(parts, chunks):
+    """torch.cat(parts, dim=1) straight into tile layout: one gf_tl_pack per part over its own column range (column offsets are multiples of 8)"""
+    M = parts[0].shape[0]
+    out = _tiles(M, chunks, parts[0].device)
+    col = 0
+    for i, p in enumerate(parts):
+        K = p.shape[1]
+        last = i == len(parts) - 1
+        col1 = 64 * chunks if last else col + K
+        check(_lib.lib().gf_tl_pack(ptr(p), 1 if p.dtype == torch.float16 else 0, p.stride(0), K, M, chunks, col, col1, None, ptr(out), stream_ptr()), "gf_tl_pack")
+        col += K
     return out
 
 
@@ -52,22 +76,24 @@ def _image(W, rows=None, chunks=None):
 
 
 class TcMLPFunction(torch.autograd.Function):
-    """y = W_L relu(... relu(W_0 x)); x [M, K0] fp32 or fp16, W_l fp32 [N_l, K_l]; y [M, N_L] fp32."""
+    """y = W_L relu(... relu(W_0 x)); x = cat(parts, dim=1) with parts [M, K_i] fp32 or fp16 (an expanded row stays a broadcast), W_l fp32
+    [N_l, K_l]; y [M, N_L] fp32.  apply(n_parts, *parts, *weights)."""
 
     @staticmethod
-    def forward(ctx, x, *weights):
+    def forward(ctx, n_parts, *args):
         _lib.require_cuda()
         L = _lib.lib()
-        x = x.detach()
-        if x.dtype not in (torch.float32, torch.float16):
-            x = x.float()
-        if x.stride(-1) != 1:
-            x = x.contiguous()
+        parts = [_prep(p) for p in args[:n_parts]]
+        weights = args[n_parts:]
         ws = [w.detach().float().contiguous() for w in weights]
-        M, K0 = x.shape
+        M, K0 = parts[0].shape[0], sum(p.shape[1] for p in parts)
         dims = [K0] + [w.shape[0] for w in ws]
         assert supported(dims), "TcMLPFunction: layer widths outside the tensor-core envelope"
-        acts = [_pack(x, K0, _chunks(K0))]                     # tile-major fp16 inputs of every layer (saved for backward)
+        assert all(p.shape[0] == M for p in parts)
+        ctx.part_cols = [p.shape[1] for p in parts]
+        ctx.part_dtypes = [p.dtype for p in parts]
+        x = parts[0]
+        acts = [_pack_parts(parts, _chunks(K0))]               # tile-major fp16 inputs of every layer (saved for backward)
         imgs = []
         # fp32 rows leave the kernels with 16-byte stores: the pitch of an odd-width output is padded to a multiple of 4 (the caller sees a view)
         n_out, ld_y = dims[-1], (dims[-1] + 3) // 4 * 4
@@ -87,7 +113,6 @@ class TcMLPFunction(torch.autograd.Function):
                 check(L.gf_tl_gemm(ptr(acts[l]), chunks, ptr(img), rows, chunks, 0, M, ptr(h), 2, 1, None, 0, None, 0, 0, None, stream_ptr()), "gf_tl_gemm(forward)")
                 acts.append(h)
         ctx.acts, ctx.imgs, ctx.dims, ctx.M = acts, imgs, dims, M
-        ctx.x_grad = x.dtype
         return y
 
     @staticmethod
@@ -125,18 +150,30 @@ class TcMLPFunction(torch.autograd.Function):
                 gn = _tiles(M, 2, dev)
                 check(L.gf_tl_gemm(ptr(g), g_chunks, ptr(img), rows, chunks, 1, M, ptr(gn), 2, 0, ptr(acts[l]), 2, None, 0, 0, None, stream_ptr()), "gf_tl_gemm(dgrad)")
                 g, g_chunks = gn, 2
-            elif ctx.needs_input_grad[0]:
+            elif any(ctx.needs_input_grad[1:1 + len(ctx.part_cols)]):
                 ld_x = (K_l + 3) // 4 * 4
                 dx_full = torch.empty(M, ld_x, dtype=torch.float32, device=dev)
                 check(L.gf_tl_gemm(ptr(g), g_chunks, ptr(img), rows, chunks, 1, M, None, 0, 0, None, 0, ptr(dx_full), ld_x, min(ld_x, 64 * chunks), ptr(inv), stream_ptr()),
                       "gf_tl_gemm(grad_input)")
                 dx = dx_full[:, :K_l]
-                if ctx.x_grad == torch.float16:
-                    dx = dx.half()
-        return (dx, *grads_w)
+        # the gradient of the concatenated input goes back to its parts as column slices (a broadcast part's expand() sums it in autograd)
+        gparts, col = [], 0
+        for i, k in enumerate(ctx.part_cols):
+            gp = None
+            if dx is not None and ctx.needs_input_grad[1 + i]:
+                gp = dx[:, col:col + k]
+                if ctx.part_dtypes[i] == torch.float16:
+                    gp = gp.half()
+            gparts.append(gp)
+            col += k
+        return (None, *gparts, *grads_w)
 
 
 def tc_mlp(x, weights):
-    if x.shape[0] == 0:                      # no samples: keep the graph, nothing to launch
-        return x.new_zeros(0, weights[-1].shape[0], dtype=torch.float32) + 0.0 * sum(w.sum() for w in weights)
-    return TcMLPFunction.apply(x, *weights)
+    """x: one [M, K] tensor or a list of parts to be concatenated along dim 1 (parts other than the last must be a multiple of 8 columns wide)"""
+    parts = list(x) if isinstance(x, (list, tuple)) else [x]
+    if any(p.shape[1] % 8 for p in parts[:-1]):
+        parts = [torch.cat(parts, dim=1)]
+    if parts[0].shape[0] == 0:               # no samples: keep the graph, nothing to launch
+        return parts[0].new_zeros(0, weights[-1].shape[0], dtype=torch.float32) + 0.0 * sum(w.sum() for w in weights)
+    return TcMLPFunction.apply(len(parts), *parts, *weights)

@@ -195,9 +195,11 @@ GF_API int gf_adnerf_mlp_forward(const GfAdnerfMlp* m, const float* rays_o, cons
  * ([tile][chunk][128 rows x 128 B, 16-byte units XOR-swizzled by row & 7]); gf_tl_tiles_bytes gives the size.
  * ------------------------------------------------------------------------------------ */
 GF_API size_t gf_tl_tiles_bytes(uint32_t M, uint32_t chunks);
-/* rows [M][ld] (fp32, or fp16 if src_f16) columns [0, K) (x *scale if non-NULL, a device scalar) -> tiles of `chunks` chunks, zero padded */
-GF_API int gf_tl_pack(const void* src, int src_f16, uint32_t ld, uint32_t K, uint32_t M, uint32_t chunks, const float* scale, void* tiles,
-                      gf_stream_t stream);
+/* rows [M][ld] (fp32, or fp16 if src_f16; ld = 0: one row broadcast to all samples) columns [0, K) (x *scale if non-NULL, a device scalar) -> columns
+ * [col0, col0 + K) of tiles with `chunks` chunks; the rest of [col0, col1) is zero filled (col1 = 0: up to the tile width); col0, col1 % 8 == 0.
+ * Calls with adjacent column ranges assemble torch.cat([...], dim=1) inputs (radnerf.py:79,90,99) without materialising them. */
+GF_API int gf_tl_pack(const void* src, int src_f16, uint32_t ld, uint32_t K, uint32_t M, uint32_t chunks, uint32_t col0, uint32_t col1,
+                      const float* scale, void* tiles, gf_stream_t stream);
 /* W [N][K] fp32 (nn.Linear.weight) -> fp16 image of `chunks` blocks [rows_pad x 128 B]; rows_pad % 16 == 0, >= N, <= 256 */
 GF_API int gf_tl_weight_image(const float* W, uint32_t N, uint32_t K, uint32_t rows_pad, uint32_t chunks, void* img, gf_stream_t stream);
 /* dgrad = 0: D = A W^T (F.linear forward; D has rows_pad columns); dgrad = 1: D = A W (grad_input; D has 64 * w_chunks columns).

@@ -313,8 +313,8 @@ def test_render_sequence_checkpoint_unwrap_and_background_options():
 
 
 def test_training_mlp_backend_selection_and_envelope():
-    """hparams['train_mlp_backend'] reaches the three field MLPs; the tensor-core envelope covers exactly the head field's nets (cond_encoder.py:92-111 /
-    radnerf.py:73-105 shapes) and not the 64/32-wide torso nets; on the CPU (no grad-capable CUDA input) MLP.forward stays on the library path and
+    """hparams['train_mlp_backend'] reaches the three field MLPs; the tensor-core envelope covers the head field's nets (cond_encoder.py:92-111 /
+    radnerf.py:73-105 shapes) and, zero-padded to the 128-row tile, the 64/32-wide torso nets; a list input stands for torch.cat(parts, 1); on the CPU (no grad-capable CUDA input) MLP.forward stays on the library path and
     equals the plain Linear/ReLU stack; the tensor-core function itself refuses to run without a GPU."""
     import torch
     from geneface_b200 import synthetic, tc_linear
@@ -326,8 +326,9 @@ def test_training_mlp_backend_selection_and_envelope():
     assert all(tc_linear.supported(n._dims()) for n in nets)
     assert RADNeRF(synthetic.may_hparams()).sigma_net.backend == 'torch'
     t = RADNeRFTorso(synthetic.may_hparams(train_mlp_backend='tc'))
-    assert not tc_linear.supported(t.torso_deform_net._dims()) and not tc_linear.supported(t.torso_canonicial_net._dims())
+    assert tc_linear.supported(t.torso_deform_net._dims()) and tc_linear.supported(t.torso_canonicial_net._dims())
     assert not tc_linear.supported([96, 128]) and not tc_linear.supported([300, 128, 3]) and not tc_linear.supported([64, 128, 200])
+    assert not tc_linear.supported([64, 256, 3]) and not tc_linear.supported([64, 8, 3])
     x = torch.randn(10, 96, requires_grad=True)
     y = m.ambient_net(x)                                  # CPU tensor: library path even with backend = 'tc'
     h = x
@@ -336,6 +337,8 @@ def test_training_mlp_backend_selection_and_envelope():
         if l != 2:
             h = torch.relu(h)
     assert torch.equal(y, h)
+    cond = torch.randn(1, 64)
+    assert torch.equal(m.ambient_net([x[:, :32], cond.expand(10, -1)]), m.ambient_net(torch.cat([x[:, :32], cond.repeat(10, 1)], dim=1)))
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             tc_linear.tc_mlp(x, [layer.weight for layer in m.ambient_net.net])

@@ -136,3 +136,31 @@ def test_train_step_with_tc_backend_matches_the_library_backend():
         assert err < 0.4, f"{n}: {err:.2e}"
     print("whole-step gradients vs fp32: tensor-core backend worst %.2e, library path under autocast worst %.2e (relative Frobenius); loss %.6f / %.6f / %.6f"
           % (worst, worst_a, l0, la, l1))
+
+
+def test_tc_mlp_takes_the_pieces_of_a_concatenated_input():
+    """tc_mlp([a, b.expand(M, -1), c], W) == tc_mlp(torch.cat([a, b.repeat(M, 1), c], 1), W) bit for bit (the pieces are packed into the same tiles),
+    gradients included; the broadcast piece's gradient arrives summed over the samples"""
+    from geneface_b200 import tc_linear
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M = 2000
+    a = torch.randn(M, 16, device="cuda", generator=g)
+    b = torch.randn(1, 128, device="cuda", generator=g)
+    c = torch.randn(1, 4, device="cuda", generator=g)
+    ws = [torch.randn(128, 148, device="cuda", generator=g) / 12, torch.randn(3, 128, device="cuda", generator=g) / 11]
+    dy = torch.randn(M, 3, device="cuda", generator=g)
+    res = []
+    for mode in ("parts", "cat"):
+        a1, b1, c1 = (t.clone().requires_grad_(True) for t in (a, b, c))
+        w1 = [w.clone().requires_grad_(True) for w in ws]
+        if mode == "parts":
+            y = tc_linear.tc_mlp([a1, b1.expand(M, -1), c1.expand(M, -1)], w1)
+        else:
+            y = tc_linear.tc_mlp(torch.cat([a1, b1.repeat(M, 1), c1.repeat(M, 1)], dim=1), w1)
+        y.backward(dy)
+        res.append((y.detach(), a1.grad, b1.grad, c1.grad, w1[0].grad, w1[1].grad))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    for i in (2, 3):                      # sums over M samples in different orders
+        assert torch.allclose(res[0][i], res[1][i], rtol=1e-4, atol=1e-5 * res[1][i].abs().max().item())
+    for i in (4, 5):                      # reductions in arbitrary order
+        assert torch.allclose(res[0][i], res[1][i], rtol=1e-4, atol=1e-5 * res[1][i].abs().max().item())
