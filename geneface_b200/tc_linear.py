@@ -92,12 +92,12 @@ class TcMLPFunction(torch.autograd.Function):
         assert all(p.shape[0] == M for p in parts)
         ctx.part_cols = [p.shape[1] for p in parts]
         ctx.part_dtypes = [p.dtype for p in parts]
-        x = parts[0]
+        dev = parts[0].device
         acts = [_pack_parts(parts, _chunks(K0))]               # tile-major fp16 inputs of every layer (saved for backward)
         imgs = []
         # fp32 rows leave the kernels with 16-byte stores: the pitch of an odd-width output is padded to a multiple of 4 (the caller sees a view)
         n_out, ld_y = dims[-1], (dims[-1] + 3) // 4 * 4
-        y_full = torch.empty(M, ld_y, dtype=torch.float32, device=x.device)
+        y_full = torch.empty(M, ld_y, dtype=torch.float32, device=dev)
         y = y_full[:, :n_out]
         for l, w in enumerate(ws):
             last = l == len(ws) - 1
@@ -109,7 +109,7 @@ class TcMLPFunction(torch.autograd.Function):
                 check(L.gf_tl_gemm(ptr(acts[l]), chunks, ptr(img), rows, chunks, 0, M, None, 0, 0, None, 0, ptr(y_full), ld_y, min(ld_y, rows), None, stream_ptr()),
                       "gf_tl_gemm(forward, output layer)")
             else:
-                h = _tiles(M, 2, x.device)
+                h = _tiles(M, 2, dev)
                 check(L.gf_tl_gemm(ptr(acts[l]), chunks, ptr(img), rows, chunks, 0, M, ptr(h), 2, 1, None, 0, None, 0, 0, None, stream_ptr()), "gf_tl_gemm(forward)")
                 acts.append(h)
         ctx.acts, ctx.imgs, ctx.dims, ctx.M = acts, imgs, dims, M
